@@ -1,0 +1,746 @@
+// C ABI of libagb.so: context, weight packing by checkpoint key, forward orchestration.
+// Mirrors (reference): CLIP_VIT_LARGE / HUBERT_LARGE wrappers (A/my_affectgpt/models/encoder.py:177-208,
+// 395-432) over HF CLIPVisionTransformer / HubertModel, and AffectGPT's fusion heads + projectors
+// (A/my_affectgpt/models/affectgpt.py:505-535, 690-716, 883-908).
+#include <atomic>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/agb.h"
+#include "agb_internal.h"
+
+namespace agb {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const std::string& get_error() { return g_error; }
+std::atomic<long long> g_launches{0};
+
+}  // namespace agb
+
+using namespace agb;
+
+namespace {
+
+struct EncLayerW {
+  bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *lnA_g = nullptr, *lnA_b = nullptr, *lnB_g = nullptr, *lnB_b = nullptr;
+};
+
+struct Loader {
+  std::vector<int64_t> shape;
+  std::function<int(const float*, cudaStream_t)> fn;
+  bool loaded = false;
+};
+
+struct Tap {
+  void* dst;
+  int64_t cap;
+};
+
+}  // namespace
+
+struct agb_ctx {
+  int device = 0;
+  agb_cfg cfg{};
+  std::string err;
+  std::vector<void*> allocs;
+  std::map<std::string, Loader> loaders;
+  std::map<std::string, Tap> taps;
+
+  // ---- CLIP ViT-L/14
+  bf16* v_patch_w = nullptr;  // [1024, 640]
+  float *v_cls = nullptr, *v_pos = nullptr, *v_pre_g = nullptr, *v_pre_b = nullptr, *v_post_g = nullptr, *v_post_b = nullptr;
+  bf16* v_proj = nullptr;  // [768, 1024]
+  std::vector<EncLayerW> v_layers;
+  // ---- HuBERT-large
+  float* h_conv0_w = nullptr;  // [512,10]
+  float *h_conv_b[7] = {}, *h_conv_g[7] = {}, *h_conv_be[7] = {};
+  bf16* h_conv_w[7] = {};  // 1..6 packed [512, k*512]
+  float *h_fp_g = nullptr, *h_fp_b = nullptr, *h_fp_bias = nullptr;
+  bf16* h_fp_w = nullptr;  // [1024,512]
+  float *h_pos_v = nullptr, *h_pos_g = nullptr, *h_pos_bias = nullptr, *h_pos_norm = nullptr;
+  bf16* h_pos_w = nullptr;  // [1024, 8192]
+  bool h_pos_v_loaded = false, h_pos_g_loaded = false, h_pos_packed = false;
+  float *h_enc_g = nullptr, *h_enc_b = nullptr;
+  std::vector<EncLayerW> h_layers;
+  // ---- fusion heads / projectors (fp32)
+  std::map<std::string, float*> f;
+
+  // ---- workspaces
+  int64_t v_cap = 0;  // frames
+  bf16 *v_apatch = nullptr, *v_xln = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_h1 = nullptr, *v_clsln = nullptr;
+  float *v_patch_out = nullptr, *v_resid = nullptr;
+  int64_t h_cap = 0;  // segments
+  bf16 *h_c0 = nullptr, *h_c1 = nullptr, *h_xln = nullptr, *h_qkv = nullptr, *h_attn = nullptr, *h_h1 = nullptr;
+  float *h_resid = nullptr, *h_stats = nullptr;
+  double *h_stat_acc = nullptr, *h_gn_acc = nullptr;
+  int64_t h_stat_cap = 0;
+  int64_t f_cap = 0;
+  float *f_a = nullptr, *f_b = nullptr, *f_c = nullptr, *f_d = nullptr, *f_e = nullptr;
+};
+
+namespace {
+
+int fail(agb_ctx* c, int code) {
+  if (c) c->err = get_error();
+  return code;
+}
+
+template <typename T>
+int dev_alloc(agb_ctx* c, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  AGB_CHECK_CUDA(cudaMalloc(&q, count * sizeof(T)));
+  if (zero) AGB_CHECK_CUDA(cudaMemset(q, 0, count * sizeof(T)));
+  c->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+int dev_free(agb_ctx* c, void* p) {
+  if (!p) return 0;
+  for (auto it = c->allocs.begin(); it != c->allocs.end(); ++it)
+    if (*it == p) {
+      c->allocs.erase(it);
+      break;
+    }
+  cudaFree(p);
+  return 0;
+}
+
+void add_loader(agb_ctx* c, const std::string& name, std::vector<int64_t> shape,
+                std::function<int(const float*, cudaStream_t)> fn) {
+  Loader l;
+  l.shape = std::move(shape);
+  l.fn = std::move(fn);
+  c->loaders[name] = std::move(l);
+}
+
+int64_t numel(const std::vector<int64_t>& s) {
+  int64_t n = 1;
+  for (auto d : s) n *= d;
+  return n;
+}
+
+// plain fp32 copy into a freshly allocated buffer
+int reg_f32(agb_ctx* c, const std::string& name, std::vector<int64_t> shape, float** slot) {
+  const int64_t n = numel(shape);
+  if (int r = dev_alloc(c, slot, (size_t)n)) return r;
+  float* dst = *slot;
+  add_loader(c, name, shape, [dst, n](const float* src, cudaStream_t s) -> int {
+    AGB_CHECK_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+  });
+  return 0;
+}
+
+// fp32 [rows, cols] -> bf16 rows of an existing matrix (row offset, row stride ld, zero pad to cols_pad)
+void reg_bf16_rows(agb_ctx* c, const std::string& name, std::vector<int64_t> shape, bf16* dst, int64_t rows, int64_t cols,
+                   int64_t ld, int64_t cols_pad) {
+  add_loader(c, name, std::move(shape), [=](const float* src, cudaStream_t s) -> int {
+    return pack_rows_f32_to_bf16(src, rows, cols, dst, ld, cols_pad, s);
+  });
+}
+
+int reg_encoder_layer(agb_ctx* c, const std::string& prefix, EncLayerW& L, const char* attn, const char* lnA,
+                      const char* lnB, const char* fc1, const char* fc2) {
+  if (int r = dev_alloc(c, &L.wqkv, 3072ull * 1024)) return r;
+  if (int r = dev_alloc(c, &L.wo, 1024ull * 1024)) return r;
+  if (int r = dev_alloc(c, &L.w1, 4096ull * 1024)) return r;
+  if (int r = dev_alloc(c, &L.w2, 1024ull * 4096)) return r;
+  if (int r = dev_alloc(c, &L.bqkv, 3072)) return r;
+  const char* qkv[3] = {"q_proj", "k_proj", "v_proj"};
+  for (int i = 0; i < 3; ++i) {
+    reg_bf16_rows(c, prefix + attn + "." + qkv[i] + ".weight", {1024, 1024}, L.wqkv + (size_t)i * 1024 * 1024, 1024, 1024,
+                  1024, 1024);
+    float* bdst = L.bqkv + i * 1024;
+    add_loader(c, prefix + attn + "." + qkv[i] + ".bias", {1024}, [bdst](const float* src, cudaStream_t s) -> int {
+      AGB_CHECK_CUDA(cudaMemcpyAsync(bdst, src, 1024 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return 0;
+    });
+  }
+  reg_bf16_rows(c, prefix + attn + ".out_proj.weight", {1024, 1024}, L.wo, 1024, 1024, 1024, 1024);
+  if (int r = reg_f32(c, prefix + attn + ".out_proj.bias", {1024}, &L.bo)) return r;
+  reg_bf16_rows(c, prefix + fc1 + ".weight", {4096, 1024}, L.w1, 4096, 1024, 1024, 1024);
+  if (int r = reg_f32(c, prefix + fc1 + ".bias", {4096}, &L.b1)) return r;
+  reg_bf16_rows(c, prefix + fc2 + ".weight", {1024, 4096}, L.w2, 1024, 4096, 4096, 4096);
+  if (int r = reg_f32(c, prefix + fc2 + ".bias", {1024}, &L.b2)) return r;
+  if (int r = reg_f32(c, prefix + lnA + ".weight", {1024}, &L.lnA_g)) return r;
+  if (int r = reg_f32(c, prefix + lnA + ".bias", {1024}, &L.lnA_b)) return r;
+  if (int r = reg_f32(c, prefix + lnB + ".weight", {1024}, &L.lnB_g)) return r;
+  if (int r = reg_f32(c, prefix + lnB + ".bias", {1024}, &L.lnB_b)) return r;
+  return 0;
+}
+
+int maybe_pack_posconv(agb_ctx* c, cudaStream_t s) {
+  if (c->h_pos_v_loaded && c->h_pos_g_loaded) {
+    if (int r = pack_posconv_weight(c->h_pos_v, c->h_pos_g, c->h_pos_w, c->h_pos_norm, s)) return r;
+    c->h_pos_packed = true;
+  }
+  return 0;
+}
+
+int register_weights(agb_ctx* c) {
+  // ------------------------------------------------------------------ CLIP
+  const std::string V = "clip.vision_model.";
+  if (int r = dev_alloc(c, &c->v_patch_w, 1024ull * 640)) return r;
+  reg_bf16_rows(c, V + "embeddings.patch_embedding.weight", {1024, 3, 14, 14}, c->v_patch_w, 1024, 588, 640, 640);
+  if (int r = reg_f32(c, V + "embeddings.class_embedding", {1024}, &c->v_cls)) return r;
+  if (int r = reg_f32(c, V + "embeddings.position_embedding.weight", {257, 1024}, &c->v_pos)) return r;
+  if (int r = reg_f32(c, V + "pre_layrnorm.weight", {1024}, &c->v_pre_g)) return r;
+  if (int r = reg_f32(c, V + "pre_layrnorm.bias", {1024}, &c->v_pre_b)) return r;
+  if (int r = reg_f32(c, V + "post_layernorm.weight", {1024}, &c->v_post_g)) return r;
+  if (int r = reg_f32(c, V + "post_layernorm.bias", {1024}, &c->v_post_b)) return r;
+  if (int r = dev_alloc(c, &c->v_proj, 768ull * 1024)) return r;
+  reg_bf16_rows(c, "clip.visual_projection.weight", {768, 1024}, c->v_proj, 768, 1024, 1024, 1024);
+  c->v_layers.resize(c->cfg.vit_layers);
+  for (int i = 0; i < c->cfg.vit_layers; ++i)
+    if (int r = reg_encoder_layer(c, V + "encoder.layers." + std::to_string(i) + ".", c->v_layers[i], "self_attn",
+                                  "layer_norm1", "layer_norm2", "mlp.fc1", "mlp.fc2"))
+      return r;
+
+  // ------------------------------------------------------------------ HuBERT
+  const std::string H = "hubert.";
+  const int kk[7] = {10, 3, 3, 3, 3, 2, 2};
+  for (int i = 0; i < 7; ++i) {
+    const std::string p = H + "feature_extractor.conv_layers." + std::to_string(i) + ".";
+    if (i == 0) {
+      if (int r = reg_f32(c, p + "conv.weight", {512, 1, 10}, &c->h_conv0_w)) return r;
+    } else {
+      if (int r = dev_alloc(c, &c->h_conv_w[i], 512ull * 512 * kk[i])) return r;
+      bf16* dst = c->h_conv_w[i];
+      const int k = kk[i];
+      add_loader(c, p + "conv.weight", {512, 512, k},
+                 [dst, k](const float* src, cudaStream_t s) -> int { return pack_conv_weight(src, k, dst, s); });
+    }
+    if (int r = reg_f32(c, p + "conv.bias", {512}, &c->h_conv_b[i])) return r;
+    const bool has_norm = c->cfg.hubert_conv_norm == 0 || i == 0;
+    if (has_norm) {
+      if (int r = reg_f32(c, p + "layer_norm.weight", {512}, &c->h_conv_g[i])) return r;
+      if (int r = reg_f32(c, p + "layer_norm.bias", {512}, &c->h_conv_be[i])) return r;
+    }
+  }
+  if (int r = reg_f32(c, H + "feature_projection.layer_norm.weight", {512}, &c->h_fp_g)) return r;
+  if (int r = reg_f32(c, H + "feature_projection.layer_norm.bias", {512}, &c->h_fp_b)) return r;
+  if (int r = dev_alloc(c, &c->h_fp_w, 1024ull * 512)) return r;
+  reg_bf16_rows(c, H + "feature_projection.projection.weight", {1024, 512}, c->h_fp_w, 1024, 512, 512, 512);
+  if (int r = reg_f32(c, H + "feature_projection.projection.bias", {1024}, &c->h_fp_bias)) return r;
+  if (int r = reg_f32(c, H + "encoder.pos_conv_embed.conv.bias", {1024}, &c->h_pos_bias)) return r;
+  if (int r = dev_alloc(c, &c->h_pos_v, 1024ull * 64 * 128)) return r;
+  if (int r = dev_alloc(c, &c->h_pos_g, 128)) return r;
+  if (int r = dev_alloc(c, &c->h_pos_norm, 128)) return r;
+  if (int r = dev_alloc(c, &c->h_pos_w, 1024ull * 8192)) return r;
+  {
+    // weight-norm parametrisation: original0 = g [1,1,128], original1 = v [1024,64,128]
+    // (transformers 4.x checkpoints name them weight_g / weight_v; both spellings fill the same slot)
+    agb_ctx* cc = c;
+    auto load_g = [cc](const float* src, cudaStream_t s) -> int {
+      AGB_CHECK_CUDA(cudaMemcpyAsync(cc->h_pos_g, src, 128 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      cc->h_pos_g_loaded = true;
+      return maybe_pack_posconv(cc, s);
+    };
+    auto load_v = [cc](const float* src, cudaStream_t s) -> int {
+      AGB_CHECK_CUDA(cudaMemcpyAsync(cc->h_pos_v, src, 1024ull * 64 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      cc->h_pos_v_loaded = true;
+      return maybe_pack_posconv(cc, s);
+    };
+    add_loader(c, H + "encoder.pos_conv_embed.conv.parametrizations.weight.original0", {1, 1, 128}, load_g);
+    add_loader(c, H + "encoder.pos_conv_embed.conv.parametrizations.weight.original1", {1024, 64, 128}, load_v);
+  }
+  if (int r = reg_f32(c, H + "encoder.layer_norm.weight", {1024}, &c->h_enc_g)) return r;
+  if (int r = reg_f32(c, H + "encoder.layer_norm.bias", {1024}, &c->h_enc_b)) return r;
+  c->h_layers.resize(c->cfg.hubert_layers);
+  for (int i = 0; i < c->cfg.hubert_layers; ++i)
+    if (int r = reg_encoder_layer(c, H + "encoder.layers." + std::to_string(i) + ".", c->h_layers[i], "attention",
+                                  "layer_norm", "final_layer_norm", "feed_forward.intermediate_dense",
+                                  "feed_forward.output_dense"))
+      return r;
+
+  // ------------------------------------------------------------------ fusion heads / projectors
+  const int D = c->cfg.llm_dim;
+  struct FS { const char* name; int out, in; };
+  const FS fs[] = {{"video_attention_mlp", 1, 768},   {"affectgpt_proj", D, 768},     {"audio_attention_mlp", 1, 1024},
+                   {"audio_llama_proj", D, 1024},     {"multi_video_embs", 1024, 768}, {"multi_audio_embs", 1024, 1024},
+                   {"attention_mlp", 1024, 2048},     {"fc_att", 2, 1024},             {"multi_llama_proj", D, 1024}};
+  for (const FS& e : fs) {
+    if (int r = reg_f32(c, std::string("fusion.") + e.name + ".weight", {e.out, e.in}, &c->f[std::string(e.name) + ".weight"])) return r;
+    if (int r = reg_f32(c, std::string("fusion.") + e.name + ".bias", {e.out}, &c->f[std::string(e.name) + ".bias"])) return r;
+  }
+  return 0;
+}
+
+int check_family_loaded(agb_ctx* c, const std::string& family) {
+  for (auto& kv : c->loaders)
+    if (kv.first.compare(0, family.size() + 1, family + ".") == 0 && !kv.second.loaded) {
+      set_error("weights not loaded: " + kv.first + " (and possibly more; see agb_missing_count)");
+      return 4;
+    }
+  return 0;
+}
+
+void tap(agb_ctx* c, const std::string& name, const void* src, int64_t bytes, cudaStream_t s) {
+  auto it = c->taps.find(name);
+  if (it == c->taps.end() || it->second.dst == nullptr) return;
+  const int64_t n = bytes < it->second.cap ? bytes : it->second.cap;
+  cudaMemcpyAsync(it->second.dst, src, (size_t)n, cudaMemcpyDeviceToDevice, s);
+}
+
+// ------------------------------------------------------------------------------------ workspaces
+int ensure_vit_ws(agb_ctx* c, int64_t frames) {
+  if (frames <= c->v_cap) return 0;
+  void* old[] = {c->v_apatch, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, c->v_clsln, c->v_patch_out, c->v_resid};
+  for (void* p : old) dev_free(c, p);
+  c->v_cap = 0;
+  const size_t M = (size_t)frames * 257;
+  if (int r = dev_alloc(c, &c->v_apatch, (size_t)frames * 256 * 640)) return r;
+  if (int r = dev_alloc(c, &c->v_patch_out, (size_t)frames * 256 * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_resid, M * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_xln, M * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_qkv, M * 3072)) return r;
+  if (int r = dev_alloc(c, &c->v_attn, M * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_h1, M * 4096)) return r;
+  if (int r = dev_alloc(c, &c->v_clsln, (size_t)frames * 1024)) return r;
+  c->v_cap = frames;
+  return 0;
+}
+
+int ensure_hub_ws(agb_ctx* c, int64_t segs) {
+  if (segs <= c->h_cap) return 0;
+  void* old[] = {c->h_c0, c->h_c1, c->h_xln, c->h_qkv, c->h_attn, c->h_h1, c->h_resid, c->h_gn_acc};
+  for (void* p : old) dev_free(c, p);
+  c->h_cap = 0;
+  const size_t M = (size_t)segs * 100;
+  if (int r = dev_alloc(c, &c->h_c0, (size_t)segs * 6400 * 512 + 4096)) return r;
+  if (int r = dev_alloc(c, &c->h_c1, (size_t)segs * 3200 * 512 + 4096)) return r;
+  if (int r = dev_alloc(c, &c->h_resid, M * 1024)) return r;
+  if (int r = dev_alloc(c, &c->h_xln, M * 1024)) return r;
+  if (int r = dev_alloc(c, &c->h_qkv, M * 3072)) return r;
+  if (int r = dev_alloc(c, &c->h_attn, M * 1024)) return r;
+  if (int r = dev_alloc(c, &c->h_h1, M * 4096)) return r;
+  if (c->cfg.hubert_conv_norm == 1)
+    if (int r = dev_alloc(c, &c->h_gn_acc, (size_t)segs * 1024)) return r;
+  c->h_cap = segs;
+  return 0;
+}
+
+int ensure_stats(agb_ctx* c, int64_t groups) {
+  if (groups <= c->h_stat_cap) return 0;
+  dev_free(c, c->h_stats);
+  dev_free(c, c->h_stat_acc);
+  if (int r = dev_alloc(c, &c->h_stats, (size_t)groups * 2)) return r;
+  if (int r = dev_alloc(c, &c->h_stat_acc, (size_t)groups * 2)) return r;
+  c->h_stat_cap = groups;
+  return 0;
+}
+
+int ensure_fuse_ws(agb_ctx* c, int64_t B) {
+  if (B <= c->f_cap) return 0;
+  void* old[] = {c->f_a, c->f_b, c->f_c, c->f_d, c->f_e};
+  for (void* p : old) dev_free(c, p);
+  if (int r = dev_alloc(c, &c->f_a, (size_t)B * 1024)) return r;
+  if (int r = dev_alloc(c, &c->f_b, (size_t)B * 1024)) return r;
+  if (int r = dev_alloc(c, &c->f_c, (size_t)B * 2048)) return r;
+  if (int r = dev_alloc(c, &c->f_d, (size_t)B * 1024)) return r;
+  if (int r = dev_alloc(c, &c->f_e, (size_t)B * 2)) return r;
+  c->f_cap = B;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ encoder block
+// pre-LN transformer block shared by CLIP (quick_gelu) and HuBERT stable-LN (erf GELU)
+int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* attn, bf16* h1, int64_t M, int nseq,
+                  int seq_stride, int seq_valid, int act, cudaStream_t s) {
+  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnA_g, L.lnA_b, 1e-5f, xln, 1024, nullptr, 0, s)) return r;
+  GemmArgs g;
+  g.A = xln; g.lda = 1024; g.W = L.wqkv; g.M = (int)M; g.N = 3072; g.K = 1024; g.bias = L.bqkv;
+  g.out_bf16 = qkv; g.ld_bf16 = 3072;
+  if (int r = gemm_bf16(g, s)) return r;
+  if (int r = attention_mha16x64(qkv, attn, nseq, seq_stride, seq_valid, 0.125f, s)) return r;
+  g = GemmArgs();
+  g.A = attn; g.lda = 1024; g.W = L.wo; g.M = (int)M; g.N = 1024; g.K = 1024; g.bias = L.bo;
+  g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024;
+  if (int r = gemm_bf16(g, s)) return r;
+  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnB_g, L.lnB_b, 1e-5f, xln, 1024, nullptr, 0, s)) return r;
+  g = GemmArgs();
+  g.A = xln; g.lda = 1024; g.W = L.w1; g.M = (int)M; g.N = 4096; g.K = 1024; g.bias = L.b1; g.act = act;
+  g.out_bf16 = h1; g.ld_bf16 = 4096;
+  if (int r = gemm_bf16(g, s)) return r;
+  g = GemmArgs();
+  g.A = h1; g.lda = 4096; g.W = L.w2; g.M = (int)M; g.N = 1024; g.K = 4096; g.bias = L.b2;
+  g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024;
+  return gemm_bf16(g, s);
+}
+
+int clip_chunk(agb_ctx* c, const void* frames, int in_dtype, int64_t F, float* out, cudaStream_t s) {
+  const int64_t M = F * 257;
+  if (int r = vit_patchify(frames, in_dtype, F, c->v_apatch, s)) return r;
+  GemmArgs g;
+  g.A = c->v_apatch; g.lda = 640; g.W = c->v_patch_w; g.M = (int)(F * 256); g.N = 1024; g.K = 640;
+  g.out_f32 = c->v_patch_out; g.ld_f32 = 1024;
+  if (int r = gemm_bf16(g, s)) return r;
+  if (int r = vit_embed_preln(c->v_patch_out, c->v_cls, c->v_pos, c->v_pre_g, c->v_pre_b, 1e-5f, F, c->v_resid, s)) return r;
+  tap(c, "vit.embed", c->v_resid, M * 1024 * 4, s);
+  for (int l = 0; l < c->cfg.vit_layers; ++l) {
+    if (int r = encoder_block(c->v_layers[l], c->v_resid, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, M, (int)F, 257, 257,
+                              ACT_QUICK_GELU, s))
+      return r;
+    tap(c, "vit.block" + std::to_string(l), c->v_resid, M * 1024 * 4, s);
+  }
+  // CLS rows -> post_layernorm -> visual_projection (no bias)   (modeling_clip.py:685-686, 860-861)
+  if (int r = layernorm_f32_in(c->v_resid, 257 * 1024, F, 1024, c->v_post_g, c->v_post_b, 1e-5f, c->v_clsln, 1024, nullptr,
+                               0, s))
+    return r;
+  g = GemmArgs();
+  g.A = c->v_clsln; g.lda = 1024; g.W = c->v_proj; g.M = (int)F; g.N = 768; g.K = 1024; g.out_f32 = out; g.ld_f32 = 768;
+  return gemm_bf16(g, s);
+}
+
+int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t spg, float* out, cudaStream_t s) {
+  const bool layer_norm = c->cfg.hubert_conv_norm == 0;
+  // conv0 (+norm +GELU) -> c0 [G*6400, 512]
+  if (int r = hubert_conv0(wav, c->h_stats, spg, seg0, G, c->h_conv0_w, c->h_conv_b[0], c->h_conv_g[0], c->h_conv_be[0],
+                           layer_norm ? 0 : 1, reinterpret_cast<float*>(c->h_gn_acc), c->h_c0, s))
+    return r;
+  // conv1..6 as GEMMs over the pair view (rows per segment: 3200, 1600, 800, 400, 200, 100)
+  bf16* src = c->h_c0;
+  bf16* dst = c->h_c1;
+  int64_t rows = 3200;
+  for (int i = 1; i <= 6; ++i) {
+    GemmArgs g;
+    g.A = src; g.W = c->h_conv_w[i]; g.M = (int)(G * rows); g.N = 512; g.bias = c->h_conv_b[i];
+    g.out_bf16 = dst; g.ld_bf16 = 512;
+    if (i <= 4) { g.mode = A_CONV3; g.K = 1536; } else { g.mode = A_PLAIN; g.K = 1024; g.lda = 1024; }
+    g.act = layer_norm ? ACT_NONE : ACT_GELU_ERF;
+    if (int r = gemm_bf16(g, s)) return r;
+    if (layer_norm)
+      if (int r = layernorm512_bf16_gelu(dst, G * rows, c->h_conv_g[i], c->h_conv_be[i], 1e-5f, true, dst, s)) return r;
+    bf16* t = src; src = dst; dst = t;
+    rows /= 2;
+  }
+  const int64_t M = G * 100;
+  tap(c, "hubert.conv", src, M * 512 * 2, s);
+  // feature projection: LN(512) -> Linear 512->1024 (fp32 residual stream + bf16 copy for the pos-conv)
+  if (int r = layernorm512_bf16_gelu(src, M, c->h_fp_g, c->h_fp_b, 1e-5f, false, dst, s)) return r;
+  GemmArgs g;
+  g.A = dst; g.lda = 512; g.W = c->h_fp_w; g.M = (int)M; g.N = 1024; g.K = 512; g.bias = c->h_fp_bias;
+  g.out_f32 = c->h_resid; g.ld_f32 = 1024; g.out_bf16 = c->h_xln; g.ld_bf16 = 1024;
+  if (int r = gemm_bf16(g, s)) return r;
+  tap(c, "hubert.featproj", c->h_resid, M * 1024 * 4, s);
+  // positional conv embedding: resid += GELU(grouped conv(resid))
+  g = GemmArgs();
+  g.mode = A_POSCONV; g.act = ACT_GELU_ERF; g.A = c->h_xln; g.W = c->h_pos_w; g.M = (int)M; g.N = 1024; g.K = 8192;
+  g.bias = c->h_pos_bias; g.res = c->h_resid; g.ld_res = 1024; g.out_f32 = c->h_resid; g.ld_f32 = 1024;
+  g.nseq = (int)G; g.seq_stride = 100; g.seq_valid = 99;
+  if (int r = gemm_bf16(g, s)) return r;
+  tap(c, "hubert.posconv", c->h_resid, M * 1024 * 4, s);
+  const int L = c->cfg.hubert_layers;
+  bool first_pool = true;
+  for (int l = 0; l < L; ++l) {
+    if (l >= L - 3) {  // hidden_states[-4], [-3], [-2] = residual stream entering layers L-3, L-2, L-1
+      if (int r = seq_mean_pool(c->h_resid, (int)G, 100, 99, nullptr, nullptr, 0.f, 0.25f, first_pool ? 0 : 1, out, s)) return r;
+      first_pool = false;
+    }
+    if (int r = encoder_block(c->h_layers[l], c->h_resid, c->h_xln, c->h_qkv, c->h_attn, c->h_h1, M, (int)G, 100, 99,
+                              ACT_GELU_ERF, s))
+      return r;
+    tap(c, "hubert.block" + std::to_string(l), c->h_resid, M * 1024 * 4, s);
+  }
+  // hidden_states[-1] = encoder.layer_norm(final residual)
+  return seq_mean_pool(c->h_resid, (int)G, 100, 99, c->h_enc_g, c->h_enc_b, 1e-5f, 0.25f, 1, out, s);
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int agb_version(void) { return AGB_VERSION; }
+
+void agb_default_cfg(agb_cfg* cfg) {
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->vit_layers = 24;
+  cfg->hubert_layers = 24;
+  cfg->hubert_conv_norm = 0;
+  cfg->hubert_do_normalize = 1;
+  cfg->llm_dim = 3584;
+  cfg->max_frames_per_chunk = 512;
+  cfg->max_segments_per_chunk = 512;
+}
+
+const char* agb_last_error(agb_ctx* ctx) {
+  (void)ctx;  // errors are recorded per calling thread; a context is single-threaded by contract
+  return get_error().c_str();
+}
+
+int agb_create(agb_ctx** out, int device, const agb_cfg* cfg) {
+  if (!out) { set_error("agb_create: null out"); return 2; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    set_error("agb_create: no CUDA device visible (this library has no CPU fallback)");
+    return 5;
+  }
+  if (device < 0 || device >= ndev) { set_error("agb_create: bad device index"); return 2; }
+  cudaDeviceProp prop;
+  AGB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error(std::string("agb_create: device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+              ", this library is built for sm_100a only");
+    return 5;
+  }
+  AGB_CHECK_CUDA(cudaSetDevice(device));
+  agb_ctx* c = new agb_ctx();
+  c->device = device;
+  if (cfg) c->cfg = *cfg; else agb_default_cfg(&c->cfg);
+  if (c->cfg.vit_layers <= 0) c->cfg.vit_layers = 24;
+  if (c->cfg.hubert_layers <= 0) c->cfg.hubert_layers = 24;
+  if (c->cfg.llm_dim <= 0) c->cfg.llm_dim = 3584;
+  if (c->cfg.max_frames_per_chunk <= 0) c->cfg.max_frames_per_chunk = 512;
+  if (c->cfg.max_segments_per_chunk <= 0) c->cfg.max_segments_per_chunk = 512;
+  if (c->cfg.hubert_layers < 3) { set_error("agb_create: hubert_layers must be >= 3 (last-4 hidden states)"); delete c; return 2; }
+  if (int r = register_weights(c)) { agb_destroy(c); return r; }
+  *out = c;
+  return 0;
+}
+
+void agb_destroy(agb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->allocs) cudaFree(p);
+  delete ctx;
+}
+
+int agb_load_tensor(agb_ctx* ctx, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
+                    void* stream) {
+  if (!ctx || !name || !dev_ptr) { set_error("agb_load_tensor: null argument"); return fail(ctx, 2); }
+  std::string key(name);
+  // transformers 4.x spelling of the weight-norm parametrisation
+  const std::string g4 = "encoder.pos_conv_embed.conv.weight_g", v4 = "encoder.pos_conv_embed.conv.weight_v";
+  if (key == "hubert." + g4) key = "hubert.encoder.pos_conv_embed.conv.parametrizations.weight.original0";
+  if (key == "hubert." + v4) key = "hubert.encoder.pos_conv_embed.conv.parametrizations.weight.original1";
+  auto it = ctx->loaders.find(key);
+  if (it == ctx->loaders.end()) { set_error("agb_load_tensor: unknown tensor name '" + key + "'"); return fail(ctx, 6); }
+  if (dtype != AGB_DTYPE_F32) { set_error("agb_load_tensor: only fp32 source tensors are accepted"); return fail(ctx, 2); }
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  if (n != numel(it->second.shape)) {
+    set_error("agb_load_tensor: element count mismatch for '" + key + "'");
+    return fail(ctx, 7);
+  }
+  if (int r = it->second.fn(static_cast<const float*>(dev_ptr), static_cast<cudaStream_t>(stream))) return fail(ctx, r);
+  it->second.loaded = true;
+  return 0;
+}
+
+int agb_missing_count(agb_ctx* ctx, const char* family) {
+  if (!ctx || !family) return -1;
+  const std::string f = std::string(family) + ".";
+  int n = 0;
+  for (auto& kv : ctx->loaders)
+    if (kv.first.compare(0, f.size(), f) == 0 && !kv.second.loaded) ++n;
+  return n;
+}
+
+const char* agb_missing_name(agb_ctx* ctx, const char* family, int index) {
+  if (!ctx || !family) return nullptr;
+  const std::string f = std::string(family) + ".";
+  int n = 0;
+  for (auto& kv : ctx->loaders)
+    if (kv.first.compare(0, f.size(), f) == 0 && !kv.second.loaded) {
+      if (n == index) return kv.first.c_str();
+      ++n;
+    }
+  return nullptr;
+}
+
+int agb_has_tensor(agb_ctx* ctx, const char* name) {
+  if (!ctx || !name) return 0;
+  return ctx->loaders.count(name) ? 1 : 0;
+}
+
+int agb_set_tap(agb_ctx* ctx, const char* name, void* dst, int64_t capacity_bytes) {
+  if (!ctx || !name) return 2;
+  if (dst == nullptr) ctx->taps.erase(name); else ctx->taps[name] = Tap{dst, capacity_bytes};
+  return 0;
+}
+
+int64_t agb_launch_count(void) { return g_launches.load(); }
+
+int agb_clip_forward(agb_ctx* ctx, const void* raw_frames, int in_dtype, int64_t n, float* out, void* stream) {
+  if (!ctx) { set_error("agb_clip_forward: null context"); return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n == 0) return 0;
+  if (n < 0 || !raw_frames || !out) { set_error("agb_clip_forward: bad arguments"); return fail(ctx, 2); }
+  if (int r = check_family_loaded(ctx, "clip")) return fail(ctx, r);
+  const int64_t cap = ctx->cfg.max_frames_per_chunk;
+  if (int r = ensure_vit_ws(ctx, n < cap ? n : cap)) return fail(ctx, r);
+  const size_t esz = in_dtype == AGB_DTYPE_U8 ? 1 : 4;
+  for (int64_t off = 0; off < n; off += cap) {
+    const int64_t F = (n - off) < cap ? (n - off) : cap;
+    const char* fp = static_cast<const char*>(raw_frames) + (size_t)off * 3 * 224 * 224 * esz;
+    if (int r = clip_chunk(ctx, fp, in_dtype, F, out + off * 768, s)) return fail(ctx, r);
+  }
+  return 0;
+}
+
+int agb_hubert_forward(agb_ctx* ctx, const float* wav, int64_t n, int64_t seg_per_norm_group, float* out, void* stream) {
+  if (!ctx) { set_error("agb_hubert_forward: null context"); return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n == 0) return 0;
+  if (n < 0 || !wav || !out) { set_error("agb_hubert_forward: bad arguments"); return fail(ctx, 2); }
+  if (int r = check_family_loaded(ctx, "hubert")) return fail(ctx, r);
+  if (!ctx->h_pos_packed) { set_error("hubert: positional conv weight-norm tensors incomplete"); return fail(ctx, 4); }
+  int64_t spg = seg_per_norm_group <= 0 ? n : seg_per_norm_group;
+  if (n % spg != 0) { set_error("agb_hubert_forward: n must be a multiple of seg_per_norm_group"); return fail(ctx, 2); }
+  const int64_t groups = n / spg;
+  if (int r = ensure_stats(ctx, groups)) return fail(ctx, r);
+  if (int r = wave_stats(wav, n, 32000, spg, ctx->h_stats, ctx->cfg.hubert_do_normalize, ctx->h_stat_acc, s)) return fail(ctx, r);
+  const int64_t cap = ctx->cfg.max_segments_per_chunk;
+  if (int r = ensure_hub_ws(ctx, n < cap ? n : cap)) return fail(ctx, r);
+  for (int64_t off = 0; off < n; off += cap) {
+    const int64_t G = (n - off) < cap ? (n - off) : cap;
+    if (int r = hubert_chunk(ctx, wav + off * 32000, off, G, spg, out + off * 1024, s)) return fail(ctx, r);
+  }
+  return 0;
+}
+
+int agb_video_fuse(agb_ctx* ctx, const float* H, int B, int T, int fusion_type, int bypass_t1, float* llm, void* stream) {
+  if (!ctx) { set_error("agb_video_fuse: null context"); return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B == 0) return 0;
+  if (int r = check_family_loaded(ctx, "fusion")) return fail(ctx, r);
+  if (int r = ensure_fuse_ws(ctx, B)) return fail(ctx, r);
+  int r;
+  if (fusion_type == AGB_FUSE_ATTENTION)
+    r = attn_pool_nosoftmax(H, B, T, 768, ctx->f["video_attention_mlp.weight"], ctx->f["video_attention_mlp.bias"], bypass_t1,
+                            ctx->f_a, s);
+  else
+    r = mean_over_t(H, B, T, 768, ctx->f_a, s);
+  if (r) return fail(ctx, r);
+  r = linear_f32(ctx->f_a, 768, ctx->f["affectgpt_proj.weight"], ctx->f["affectgpt_proj.bias"], llm, ctx->cfg.llm_dim, B,
+                 ctx->cfg.llm_dim, 768, s);
+  return r ? fail(ctx, r) : 0;
+}
+
+int agb_audio_fuse(agb_ctx* ctx, const float* H, int B, int T, int fusion_type, float* llm, void* stream) {
+  if (!ctx) { set_error("agb_audio_fuse: null context"); return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B == 0) return 0;
+  if (int r = check_family_loaded(ctx, "fusion")) return fail(ctx, r);
+  if (int r = ensure_fuse_ws(ctx, B)) return fail(ctx, r);
+  int r;
+  if (fusion_type == AGB_FUSE_ATTENTION)
+    r = attn_pool_nosoftmax(H, B, T, 1024, ctx->f["audio_attention_mlp.weight"], ctx->f["audio_attention_mlp.bias"], 0,
+                            ctx->f_a, s);
+  else
+    r = mean_over_t(H, B, T, 1024, ctx->f_a, s);
+  if (r) return fail(ctx, r);
+  r = linear_f32(ctx->f_a, 1024, ctx->f["audio_llama_proj.weight"], ctx->f["audio_llama_proj.bias"], llm, ctx->cfg.llm_dim,
+                 B, ctx->cfg.llm_dim, 1024, s);
+  return r ? fail(ctx, r) : 0;
+}
+
+int agb_multi_fuse(agb_ctx* ctx, const float* Hv, int Tv, const float* Ha, int Ta, int B, float* multi_hidden, float* llm,
+                   void* stream) {
+  if (!ctx) { set_error("agb_multi_fuse: null context"); return 2; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B == 0) return 0;
+  if (int r = check_family_loaded(ctx, "fusion")) return fail(ctx, r);
+  if (int r = ensure_fuse_ws(ctx, B)) return fail(ctx, r);
+  auto& f = ctx->f;
+  int r;
+  // v = multi_video_embs(mean_t Hv), a = multi_audio_embs(mean_t Ha)          (affectgpt.py:890-893)
+  if ((r = mean_over_t(Hv, B, Tv, 768, ctx->f_a, s))) return fail(ctx, r);
+  if ((r = mean_over_t(Ha, B, Ta, 1024, ctx->f_b, s))) return fail(ctx, r);
+  float* v = ctx->f_c;            // [B,1024] (first half of the concat buffer, row stride 2048)
+  float* a = ctx->f_c + 1024;     // second half
+  if ((r = linear_f32(ctx->f_a, 768, f["multi_video_embs.weight"], f["multi_video_embs.bias"], v, 2048, B, 1024, 768, s))) return fail(ctx, r);
+  if ((r = linear_f32(ctx->f_b, 1024, f["multi_audio_embs.weight"], f["multi_audio_embs.bias"], a, 2048, B, 1024, 1024, s))) return fail(ctx, r);
+  // att = fc_att(attention_mlp([v | a]))                                      (:895-897)
+  if ((r = linear_f32(ctx->f_c, 2048, f["attention_mlp.weight"], f["attention_mlp.bias"], ctx->f_d, 1024, B, 1024, 2048, s))) return fail(ctx, r);
+  if ((r = linear_f32(ctx->f_d, 1024, f["fc_att.weight"], f["fc_att.bias"], ctx->f_e, 2, B, 2, 1024, s))) return fail(ctx, r);
+  // multi = [v, a] . att                                                      (:900-902)
+  // (v and a live interleaved in the concat buffer with row stride 2048: copy out densely first)
+  AGB_CHECK_CUDA(cudaMemcpy2DAsync(ctx->f_a, 1024 * 4, v, 2048 * 4, 1024 * 4, B, cudaMemcpyDeviceToDevice, s));
+  AGB_CHECK_CUDA(cudaMemcpy2DAsync(ctx->f_b, 1024 * 4, a, 2048 * 4, 1024 * 4, B, cudaMemcpyDeviceToDevice, s));
+  if ((r = weighted_pair_sum(ctx->f_a, ctx->f_b, ctx->f_e, B, 1024, multi_hidden, s))) return fail(ctx, r);
+  r = linear_f32(multi_hidden, 1024, f["multi_llama_proj.weight"], f["multi_llama_proj.bias"], llm, ctx->cfg.llm_dim, B,
+                 ctx->cfg.llm_dim, 1024, s);
+  return r ? fail(ctx, r) : 0;
+}
+
+// ---- kernel-level entry points ---------------------------------------------------------------
+int agb_op_gemm(int a_mode, int act, const void* A, int64_t lda, const void* W, int M, int N, int K, const float* bias,
+                const float* res, int64_t ld_res, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, int nseq,
+                int seq_stride, int seq_valid, void* stream) {
+  GemmArgs g;
+  g.mode = a_mode; g.act = act; g.A = static_cast<const bf16*>(A); g.lda = lda; g.W = static_cast<const bf16*>(W);
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.res = res; g.ld_res = ld_res; g.out_f32 = out_f32; g.ld_f32 = ld_f32;
+  g.out_bf16 = static_cast<bf16*>(out_bf16); g.ld_bf16 = ld_bf16; g.nseq = nseq; g.seq_stride = seq_stride; g.seq_valid = seq_valid;
+  return gemm_bf16(g, static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_layernorm(const float* x, int64_t ldx, int64_t rows, int D, const float* gamma, const float* beta, float eps,
+                     void* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, void* stream) {
+  return layernorm_f32_in(x, ldx, rows, D, gamma, beta, eps, static_cast<bf16*>(out_bf16), ld_bf16, out_f32, ld_f32,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_layernorm512_bf16(const void* x, int64_t rows, const float* gamma, const float* beta, float eps, int gelu,
+                             void* out, void* stream) {
+  return layernorm512_bf16_gelu(const_cast<bf16*>(static_cast<const bf16*>(x)), rows, gamma, beta, eps, gelu != 0,
+                                static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_attention(const void* qkv, void* out, int nseq, int seq_stride, int seq_valid, float scale, void* stream) {
+  return attention_mha16x64(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), nseq, seq_stride, seq_valid, scale,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_patchify(const void* frames, int in_dtype, int64_t n, void* a_patch, void* stream) {
+  return vit_patchify(frames, in_dtype, n, static_cast<bf16*>(a_patch), static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_conv0(const float* wav, int64_t nseg, int64_t seg_per_norm_group, int do_normalize, const float* w,
+                 const float* bias, const float* gamma, const float* beta, int norm_mode, void* out, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t spg = seg_per_norm_group <= 0 ? nseg : seg_per_norm_group;
+  AGB_REQUIRE(nseg > 0 && nseg % spg == 0, "conv0: bad normalisation grouping");
+  const int64_t groups = nseg / spg;
+  float* stats = nullptr;
+  double* acc = nullptr;
+  double* gn = nullptr;
+  AGB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 2 * groups));
+  AGB_CHECK_CUDA(cudaMalloc(&acc, sizeof(double) * 2 * groups));
+  if (norm_mode == 1) AGB_CHECK_CUDA(cudaMalloc(&gn, sizeof(double) * 1024 * nseg));
+  int r = wave_stats(wav, nseg, 32000, spg, stats, do_normalize, acc, s);
+  if (!r) r = hubert_conv0(wav, stats, spg, 0, nseg, w, bias, gamma, beta, norm_mode, reinterpret_cast<float*>(gn),
+                           static_cast<bf16*>(out), s);
+  cudaStreamSynchronize(s);
+  cudaFree(stats);
+  cudaFree(acc);
+  if (gn) cudaFree(gn);
+  return r;
+}
+
+int agb_op_seq_mean_pool(const float* x, int nseq, int seq_stride, int seq_valid, const float* gamma, const float* beta,
+                         float eps, float scale, int accumulate, float* pooled, void* stream) {
+  return seq_mean_pool(x, nseq, seq_stride, seq_valid, gamma, beta, eps, scale, accumulate, pooled,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_linear_f32(const float* in, int64_t ld_in, const float* W, const float* bias, float* out, int64_t ld_out, int M,
+                      int N, int K, void* stream) {
+  return linear_f32(in, ld_in, W, bias, out, ld_out, M, N, K, static_cast<cudaStream_t>(stream));
+}
+
+int agb_op_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  return convert_f32_to_bf16(src, static_cast<bf16*>(dst), n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

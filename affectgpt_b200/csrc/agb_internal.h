@@ -1,0 +1,130 @@
+// Internal declarations shared by the .cu translation units of libagb.so (not part of the C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+
+namespace agb {
+
+using bf16 = __nv_bfloat16;
+
+// thread-local error text; the C ABI copies it into the context
+void set_error(const std::string& msg);
+const std::string& get_error();
+
+#define AGB_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      ::agb::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                       ":" + std::to_string(__LINE__) + ")");                                        \
+      return 1;                                                                                      \
+    }                                                                                                \
+  } while (0)
+
+// after every kernel launch: count it (bench.py reports gpu_launches) and surface launch errors
+extern std::atomic<long long> g_launches;
+#define AGB_CHECK_LAUNCH()                  \
+  do {                                      \
+    ++::agb::g_launches;                    \
+    AGB_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
+#define AGB_REQUIRE(cond, msg)                                                            \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      ::agb::set_error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" +             \
+                       std::to_string(__LINE__) + ")");                                   \
+      return 2;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
+enum AMode : int {
+  A_PLAIN = 0,    // A is [M, K] row-major (row stride lda elements)
+  A_CONV3 = 1,    // k=3,s=2 conv over channels-last rows of 512: A is the "pair" view [M(+1), 1024];
+                  // logical K = 1536 = pair row m (1024) ++ first half of pair row m+1 (512)
+  A_POSCONV = 2,  // grouped k=128 conv over [nseq, seq_stride, 1024]; one M tile per sequence,
+                  // one N tile (64) per group, K block kb = tap kb of that group's 64 channels
+};
+
+struct GemmArgs {
+  int mode = A_PLAIN;
+  int act = ACT_NONE;
+  const bf16* A = nullptr;
+  int64_t lda = 0;      // elements (PLAIN); ignored otherwise
+  const bf16* W = nullptr;  // [N, K] row-major (K contiguous); POSCONV: [1024, 8192]
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;  // [N] or null
+  const float* res = nullptr;   // fp32 [M, ld_res] added after activation, or null (may alias out_f32)
+  int64_t ld_res = 0;
+  float* out_f32 = nullptr;
+  int64_t ld_f32 = 0;
+  bf16* out_bf16 = nullptr;
+  int64_t ld_bf16 = 0;
+  // POSCONV only
+  int nseq = 0, seq_stride = 0, seq_valid = 0;
+};
+
+// tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns 0 on success.
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+
+// layernorm.cu ------------------------------------------------------------------------------
+// y = LN(x) * gamma + beta over the last dim (D = 1024 or 512), eps.  x fp32 or bf16 rows with
+// row stride ldx; writes bf16 and/or fp32.
+int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const float* gamma, const float* beta,
+                     float eps, bf16* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32,
+                     cudaStream_t s);
+// in-place over bf16 rows of 512 channels: y = act(LN(x)) (HuBERT conv stack, "layer" variant)
+int layernorm512_bf16_gelu(bf16* x, int64_t rows, const float* gamma, const float* beta, float eps,
+                           bool apply_gelu, bf16* out, cudaStream_t s);
+
+// attention.cu -------------------------------------------------------------------------------
+// qkv: [nseq * seq_stride, 3*1024] bf16 (q | k | v, 16 heads x 64); out: [nseq * seq_stride, 1024] bf16
+int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale,
+                       cudaStream_t s);
+
+// vit.cu -------------------------------------------------------------------------------------
+int vit_patchify(const void* frames, int in_dtype /*0=f32 0..255, 1=u8*/, int64_t nframes, bf16* a_patch /*[n*256,640]*/,
+                 cudaStream_t s);
+int vit_embed_preln(const float* patch_out /*[n*256,1024]*/, const float* cls, const float* pos,
+                    const float* g, const float* b, float eps, int64_t nframes, float* resid /*[n*257,1024]*/,
+                    cudaStream_t s);
+
+// hubert.cu ----------------------------------------------------------------------------------
+int wave_stats(const float* wav, int64_t nseg, int64_t samples, int64_t seg_per_group, float* stats /*[ngroups,2] mean,rstd*/,
+               int do_normalize, double* acc_scratch /*[ngroups,2]*/, cudaStream_t s);
+int hubert_conv0(const float* wav, const float* stats, int64_t seg_per_group, int64_t seg_offset, int64_t nseg, const float* w /*[512,10]*/,
+                 const float* bias, const float* g, const float* b, int norm_mode /*0 layer,1 group*/,
+                 float* gn_scratch /*nseg*1024 doubles, group mode only*/, bf16* out /*[nseg*6400,512]*/, cudaStream_t s);
+int gelu_bf16_inplace(bf16* x, int64_t n, cudaStream_t s);
+// pooled[seq, :] (+)= scale * mean_{t<valid} f(x[seq, t, :]); f = identity or LayerNorm(gamma,beta)
+int seq_mean_pool(const float* x, int nseq, int seq_stride, int seq_valid, const float* gamma, const float* beta,
+                  float eps, float scale, int accumulate, float* pooled /*[nseq,1024]*/, cudaStream_t s);
+
+// fusion.cu ----------------------------------------------------------------------------------
+// out[M,N] = in[M,K] @ W[N,K]^T + bias  (fp32 SIMT; the heads are ~0.03 GF per clip)
+int linear_f32(const float* in, int64_t ld_in, const float* W, const float* bias, float* out, int64_t ld_out, int M,
+               int N, int K, cudaStream_t s);
+// fused[b,:] = sum_t H[b,t,:] * (H[b,t,:].w + bias)   (no softmax: affectgpt.py:526-529)
+int attn_pool_nosoftmax(const float* H, int B, int T, int D, const float* w, const float* bias, int bypass_if_t1,
+                        float* fused, cudaStream_t s);
+int mean_over_t(const float* H, int B, int T, int D, float* out, cudaStream_t s);
+// multi[b,:] = att[b,0] * v[b,:] + att[b,1] * a[b,:]
+int weighted_pair_sum(const float* v, const float* a, const float* att, int B, int D, float* out, cudaStream_t s);
+int concat2_f32(const float* a, const float* b, int B, int Da, int Db, float* out, cudaStream_t s);
+
+// pack.cu ------------------------------------------------------------------------------------
+int convert_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
+// dst[r, c] (row stride ld_dst) = src[r, c] for r<rows, c<cols; zero-fills c in [cols, cols_pad)
+int pack_rows_f32_to_bf16(const float* src, int64_t rows, int64_t cols, bf16* dst, int64_t ld_dst, int64_t cols_pad,
+                          cudaStream_t s);
+// conv weight [512, 512, k] -> [512, k*512] with K index = tap*512 + c_in
+int pack_conv_weight(const float* src, int k, bf16* dst, cudaStream_t s);
+// pos-conv: w = g * v / ||v||_(dims 0,1) per tap; v [1024,64,128], g [128]; dst [1024, 128*64], K index = tap*64 + c_in
+int pack_posconv_weight(const float* v, const float* g, bf16* dst, float* norm_scratch /*[128]*/, cudaStream_t s);
+
+}  // namespace agb

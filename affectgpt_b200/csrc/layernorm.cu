@@ -1,0 +1,146 @@
+// Fused LayerNorm kernels (warp per row, warp-shuffle reductions, 16-byte vector I/O; HBM-bound).
+// Replaces nn.LayerNorm calls in HF CLIPEncoderLayer (modeling_clip.py:359-380), pre/post layernorm
+// (:677, :686), HubertEncoderLayerStableLayerNorm (modeling_hubert.py:505-548), the HuBERT conv-stack
+// LayerNorm + GELU (:150-175) and feature projection LayerNorm (:216-231).
+#include "agb_internal.h"
+#include "agb_ptx.cuh"
+
+namespace agb {
+
+namespace {
+
+// NV = D / 128 float4 vectors per lane
+template <int NV>
+__global__ void __launch_bounds__(256) ln_f32_kernel(const float* __restrict__ x, long long ldx, long long rows,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float eps, bf16* __restrict__ ob, long long ldb,
+                                                    float* __restrict__ of, long long ldf) {
+  constexpr int D = NV * 128;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (ob != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(y.x, y.y);
+      o.y = pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(ob + row * ldb)[lane + 32 * i] = o;
+    }
+    if (of != nullptr) reinterpret_cast<float4*>(of + row * ldf)[lane + 32 * i] = y;
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// rows of 512 bf16 channels: y = [gelu](LN(x)); warp per row, lane owns 2 x 8 channels
+__global__ void __launch_bounds__(256) ln512_bf16_kernel(const bf16* x, long long rows,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps, int apply_gelu,
+                                                        bf16* out) {  // x may alias out
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * 512);
+  float f[16];
+  unpack8(xr[lane], f);
+  unpack8(xr[lane + 32], f + 8);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += f[i];
+  const float mean = warp_sum(s) * (1.0f / 512.f);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = f[i] - mean;
+    ss += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / 512.f) + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + row * 512);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c0 = (lane + 32 * h) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      y[i] = (f[h * 8 + i] - mean) * rstd * gg[i] + bb[i];
+      if (apply_gelu) y[i] = gelu_erf(y[i]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(y[0], y[1]);
+    o.y = pack_bf16x2(y[2], y[3]);
+    o.z = pack_bf16x2(y[4], y[5]);
+    o.w = pack_bf16x2(y[6], y[7]);
+    orow[lane + 32 * h] = o;
+  }
+}
+
+}  // namespace
+
+int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const float* gamma, const float* beta, float eps,
+                     bf16* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, cudaStream_t s) {
+  AGB_REQUIRE(rows > 0, "layernorm: no rows");
+  AGB_REQUIRE(D == 512 || D == 768 || D == 1024, "layernorm: D must be 512, 768 or 1024");
+  AGB_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "layernorm: input alignment");
+  AGB_REQUIRE(out_bf16 != nullptr || out_f32 != nullptr, "layernorm: no output");
+  if (out_bf16) AGB_REQUIRE(ld_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0, "layernorm: bf16 out alignment");
+  if (out_f32) AGB_REQUIRE(ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0, "layernorm: f32 out alignment");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (D == 1024)
+    ln_f32_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
+  else if (D == 768)
+    ln_f32_kernel<6><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
+  else
+    ln_f32_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+int layernorm512_bf16_gelu(bf16* x, int64_t rows, const float* gamma, const float* beta, float eps, bool apply_gelu,
+                           bf16* out, cudaStream_t s) {
+  AGB_REQUIRE(rows > 0, "layernorm512: no rows");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  ln512_bf16_kernel<<<grid, 256, 0, s>>>(x, rows, gamma, beta, eps, apply_gelu ? 1 : 0, out);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace agb

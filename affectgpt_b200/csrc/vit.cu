@@ -1,0 +1,120 @@
+// ViT front-end kernels: CLIP preprocessing fused with im2col, and CLS/position-embedding assembly
+// fused with pre_layrnorm.
+//
+// Replaces (reference): the CPU round trip of CLIP_VIT_LARGE.forward -- per-frame .cpu() -> PIL ->
+// HF CLIP processor -> .to(device) (A/my_affectgpt/models/encoder.py:34-39, 200-204) -- and
+// CLIPVisionEmbeddings.forward + pre_layrnorm (HF modeling_clip.py:148-154, 209-217, 677).
+#include "agb_internal.h"
+#include "agb_ptx.cuh"
+
+namespace agb {
+
+namespace {
+
+__constant__ float kClipMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float kClipStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+// A_patch[(n*256 + py*16 + px), c*196 + ky*14 + kx] = ((u8)frame[n,c,py*14+ky,px*14+kx] / 255 - mean[c]) / std[c]
+// columns 588..639 are zero padding so that K is a multiple of 64 (the packed conv weight is padded too).
+template <typename TIn>
+__global__ void __launch_bounds__(256) patchify_kernel(const TIn* __restrict__ frames, long long nframes,
+                                                      bf16* __restrict__ a_patch) {
+  // one thread -> 2 consecutive K columns of one patch row
+  const long long total = nframes * 256 * 320;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(idx % 320);
+    const long long prow = idx / 320;
+    const int patch = (int)(prow & 255);
+    const long long n = prow >> 8;
+    const int py = patch >> 4, px = patch & 15;
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = kp * 2 + e;
+      if (k < 588) {
+        const int c = k / 196, r = k % 196;
+        const int ky = r / 14, kx = r % 14;
+        const long long off = ((n * 3 + c) * 224 + (py * 14 + ky)) * 224 + (px * 14 + kx);
+        float x = (float)frames[off];
+        // Image.fromarray(frame.astype(np.uint8)): truncation toward zero (encoder.py:37)
+        x = truncf(x);
+        x = fminf(fmaxf(x, 0.f), 255.f);
+        v[e] = (x * (1.0f / 255.0f) - kClipMean[c]) / kClipStd[c];
+      } else {
+        v[e] = 0.f;
+      }
+    }
+    reinterpret_cast<uint32_t*>(a_patch)[idx] = pack_bf16x2(v[0], v[1]);
+  }
+}
+
+// resid[n*257 + tok, :] = LN_pre( (tok == 0 ? cls : patch_out[n*256 + tok - 1, :]) + pos[tok, :] )
+__global__ void __launch_bounds__(256) embed_preln_kernel(const float* __restrict__ patch_out,
+                                                         const float* __restrict__ cls,
+                                                         const float* __restrict__ pos, const float* __restrict__ g,
+                                                         const float* __restrict__ b, float eps, long long nframes,
+                                                         float* __restrict__ resid) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= nframes * 257) return;
+  const int lane = threadIdx.x & 31;
+  const long long n = row / 257;
+  const int tok = (int)(row % 257);
+  const float4* src = reinterpret_cast<const float4*>(tok == 0 ? cls : patch_out + (n * 256 + tok - 1) * 1024);
+  const float4* pr = reinterpret_cast<const float4*>(pos + (long long)tok * 1024);
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = src[lane + 32 * i], p = __ldg(pr + lane + 32 * i);
+    v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / 1024.f);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / 1024.f) + eps);
+  float4* orow = reinterpret_cast<float4*>(resid + row * 1024);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * gg.x + bb.x;
+    y.y = (v[i].y - mean) * rstd * gg.y + bb.y;
+    y.z = (v[i].z - mean) * rstd * gg.z + bb.z;
+    y.w = (v[i].w - mean) * rstd * gg.w + bb.w;
+    orow[lane + 32 * i] = y;
+  }
+}
+
+}  // namespace
+
+int vit_patchify(const void* frames, int in_dtype, int64_t nframes, bf16* a_patch, cudaStream_t s) {
+  AGB_REQUIRE(nframes > 0, "patchify: no frames");
+  AGB_REQUIRE(in_dtype == 0 || in_dtype == 1, "patchify: input dtype must be f32 (0) or u8 (1)");
+  const long long total = nframes * 256 * 320;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  if (in_dtype == 0)
+    patchify_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const float*>(frames), nframes, a_patch);
+  else
+    patchify_kernel<uint8_t><<<(unsigned)blocks, 256, 0, s>>>(static_cast<const uint8_t*>(frames), nframes, a_patch);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vit_embed_preln(const float* patch_out, const float* cls, const float* pos, const float* g, const float* b,
+                    float eps, int64_t nframes, float* resid, cudaStream_t s) {
+  AGB_REQUIRE(nframes > 0, "embed: no frames");
+  const long long rows = nframes * 257;
+  embed_preln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(patch_out, cls, pos, g, b, eps, nframes, resid);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace agb
