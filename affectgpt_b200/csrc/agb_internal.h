@@ -42,6 +42,16 @@ extern std::atomic<long long> g_launches;
     }                                                                                     \
   } while (0)
 
+// profiling categories (agb_profile_*): wrapper-level CUDA-event timing, off unless enabled
+enum ProfCat : int { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_LAYERNORM = 2, PROF_FRONTEND = 3, PROF_OTHER = 4 };
+bool profiling_on();
+struct LaunchTimer {
+  LaunchTimer(int cat, double flops, double bytes, cudaStream_t s);
+  ~LaunchTimer();
+  int idx_;
+  cudaStream_t s_;
+};
+
 enum Act : int { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
 enum AMode : int {
   A_PLAIN = 0,    // A is [M, K] row-major (row stride lda elements)

@@ -192,6 +192,8 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
   AGB_REQUIRE(nseq <= 65535, "attention: too many sequences for one launch");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
               "attention: alignment");
+  LaunchTimer timer(PROF_ATTENTION, 4.0 * nseq * 16.0 * (double)seq_valid * seq_valid * 64.0,
+                    (double)nseq * seq_valid * 4096.0 * 2.0, s);
   if (seq_valid <= 112) return launch_mha<7>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   if (seq_valid <= 272) return launch_mha<17>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   AGB_REQUIRE(false, "attention: sequence length > 272 not supported by the register-resident softmax kernel");

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) concat2_kernel(const float* __restrict__ 
 int linear_f32(const float* in, int64_t ld_in, const float* W, const float* bias, float* out, int64_t ld_out, int M, int N,
                int K, cudaStream_t s) {
   AGB_REQUIRE(M > 0 && N > 0 && K > 0, "linear: empty problem");
+  LaunchTimer timer(PROF_OTHER, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)N * K + (double)M * N), s);
   dim3 grid((N + LT_N - 1) / LT_N, (M + LT_M - 1) / LT_M);
   linear_kernel<<<grid, 256, 0, s>>>(in, ld_in, W, bias, out, ld_out, M, N, K);
   AGB_CHECK_LAUNCH();

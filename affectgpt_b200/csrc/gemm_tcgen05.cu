@@ -112,7 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           void* dA = smA + stage * C::kABytes;
           void* dB = smB + stage * C::kBBytes;
           if constexpr (MODE == A_PLAIN) {
-            tma_load_2d(dA, &tmA, &full[stage], kb * BK, mt * BM, kEvictFirst);
+            tma_load_2d(dA, &tmA, &full[stage], kb * BK, mt * BM, kEvictNormal);
             tma_load_2d(dB, &tmB, &full[stage], kb * BK, nt * BN, kEvictLast);
           } else if constexpr (MODE == A_CONV3) {
             // K blocks 0..15: pair row m, cols kb*64; K blocks 16..23: pair row m+1, cols (kb-16)*64
@@ -327,6 +327,11 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
               "gemm: operands must be 16-byte aligned");
 
+  const double rows_eff = a.mode == A_POSCONV ? (double)a.nseq * a.seq_valid : (double)a.M;
+  LaunchTimer timer(PROF_GEMM, 2.0 * rows_eff * a.N * a.K,
+                    2.0 * (rows_eff * a.K + (double)a.N * a.K) + rows_eff * a.N * (a.out_f32 ? 4.0 : 0.0) +
+                        rows_eff * a.N * (a.out_bf16 ? 2.0 : 0.0) + rows_eff * a.N * (a.res ? 4.0 : 0.0),
+                    stream);
   KParams kp{};
   kp.M = a.M; kp.N = a.N; kp.K = a.K;
   kp.bias = a.bias; kp.res = a.res; kp.ld_res = a.ld_res;

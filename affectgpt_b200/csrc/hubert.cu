@@ -309,6 +309,7 @@ int hubert_conv0(const float* wav, const float* stats, int64_t seg_per_group, in
                  cudaStream_t s) {
   AGB_REQUIRE(nseg > 0 && nseg <= 65535, "conv0: bad segment count");
   if (seg_per_group <= 0) seg_per_group = seg_offset + nseg;
+  LaunchTimer timer(PROF_FRONTEND, 2.0 * nseg * 6399.0 * 512 * 10, (double)nseg * (32000.0 * 4 + 6400.0 * 512 * 2), s);
   dim3 grid((kL0Pad + kRowsPerBlock - 1) / kRowsPerBlock, (unsigned)nseg);
   if (norm_mode == 0) {
     conv0_kernel<0><<<grid, 256, 0, s>>>(wav, stats, seg_per_group, seg_offset, w, bias, g, b, nullptr, out);
@@ -336,6 +337,7 @@ int gelu_bf16_inplace(bf16* x, int64_t n, cudaStream_t s) {
 int seq_mean_pool(const float* x, int nseq, int seq_stride, int seq_valid, const float* gamma, const float* beta,
                   float eps, float scale, int accumulate, float* pooled, cudaStream_t s) {
   AGB_REQUIRE(nseq > 0 && seq_valid > 0 && seq_valid <= seq_stride, "pool: bad shape");
+  LaunchTimer timer(PROF_FRONTEND, 0.0, (double)nseq * seq_valid * 1024 * 4.0 * (gamma ? 2 : 1), s);
   const size_t smem = sizeof(float) * (2 * seq_valid + 8 * 256);
   AGB_REQUIRE(smem <= 48 * 1024, "pool: sequence too long");
   seq_pool_kernel<<<dim3(nseq, 4), 256, smem, s>>>(x, seq_stride, seq_valid, gamma, beta, eps, scale, accumulate, pooled);

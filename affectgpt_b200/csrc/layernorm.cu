@@ -123,6 +123,7 @@ int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const flo
   AGB_REQUIRE(out_bf16 != nullptr || out_f32 != nullptr, "layernorm: no output");
   if (out_bf16) AGB_REQUIRE(ld_bf16 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0, "layernorm: bf16 out alignment");
   if (out_f32) AGB_REQUIRE(ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0, "layernorm: f32 out alignment");
+  LaunchTimer timer(PROF_LAYERNORM, 8.0 * rows * D, (double)rows * D * (4.0 + (out_bf16 ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)), s);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (D == 1024)
     ln_f32_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
@@ -137,6 +138,7 @@ int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const flo
 int layernorm512_bf16_gelu(bf16* x, int64_t rows, const float* gamma, const float* beta, float eps, bool apply_gelu,
                            bf16* out, cudaStream_t s) {
   AGB_REQUIRE(rows > 0, "layernorm512: no rows");
+  LaunchTimer timer(PROF_LAYERNORM, 8.0 * rows * 512, (double)rows * 512 * 4.0, s);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   ln512_bf16_kernel<<<grid, 256, 0, s>>>(x, rows, gamma, beta, eps, apply_gelu ? 1 : 0, out);
   AGB_CHECK_LAUNCH();

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) embed_preln_kernel(const float* __restric
 int vit_patchify(const void* frames, int in_dtype, int64_t nframes, bf16* a_patch, cudaStream_t s) {
   AGB_REQUIRE(nframes > 0, "patchify: no frames");
   AGB_REQUIRE(in_dtype == 0 || in_dtype == 1, "patchify: input dtype must be f32 (0) or u8 (1)");
+  LaunchTimer timer(PROF_FRONTEND, 0.0, (double)nframes * (150528.0 * (in_dtype == 0 ? 4 : 1) + 256.0 * 640 * 2), s);
   const long long total = nframes * 256 * 320;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 64) blocks = 148 * 64;
@@ -112,6 +113,7 @@ int vit_embed_preln(const float* patch_out, const float* cls, const float* pos, 
                     float eps, int64_t nframes, float* resid, cudaStream_t s) {
   AGB_REQUIRE(nframes > 0, "embed: no frames");
   const long long rows = nframes * 257;
+  LaunchTimer timer(PROF_LAYERNORM, 8.0 * rows * 1024, (double)rows * 1024 * 8.0, s);
   embed_preln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(patch_out, cls, pos, g, b, eps, nframes, resid);
   AGB_CHECK_LAUNCH();
   return 0;

@@ -1,0 +1,174 @@
+"""Model-side glue of the hot path: fusion heads + projectors with the reference's method names.
+
+Reference: A/my_affectgpt/models/affectgpt.py -- ``encode_video_merge`` (:537-624), ``encode_audio_merge``
+(:718-782), ``encode_multi_merge`` (:910-915) and the token set built in ``forward`` (:924-947).  Weights use the
+reference's ``ckpt['model']`` keys (``video_attention_mlp.*``, ``affectgpt_proj.*``, ``audio_attention_mlp.*``,
+``audio_llama_proj.*``, ``multi_video_embs.*``, ``multi_audio_embs.*``, ``attention_mlp.*``, ``fc_att.*``,
+``multi_llama_proj.*``; affectgpt.py:1099-1120) and are loaded non-strictly, as the reference does.
+
+Scope: the shipping ``attention`` fusion (every config in train_configs/) and ``mean``.  The Q-Former
+variants are not built yet and raise NotImplementedError (DESIGN.md "next").  The LLM, LoRA and the loss are
+out of scope: this class stops at the fused tokens.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import config
+from .encoders import CLIP_VIT_LARGE, HUBERT_LARGE
+from .engine import Engine, get_engine
+from .registry import registry
+
+FUSION_KEYS = ("video_attention_mlp", "affectgpt_proj", "audio_attention_mlp", "audio_llama_proj", "multi_video_embs",
+               "multi_audio_embs", "attention_mlp", "fc_att", "multi_llama_proj")
+
+
+@registry.register_model("affectgpt")
+class AffectGPTFusion(nn.Module):
+    def __init__(self, visual_encoder: Optional[nn.Module] = None, acoustic_encoder: Optional[nn.Module] = None,
+                 video_fusion_type: str = "attention", audio_fusion_type: str = "attention",
+                 multi_fusion_type: str = "attention", num_video_query_token: int = 1, num_audio_query_token: int = 1,
+                 num_multi_query_token: int = 1, llm_dim: int = config.LLM_DIM, engine: Optional[Engine] = None,
+                 engine_cfg: Optional[dict] = None):
+        super().__init__()
+        for name, ft in (("video", video_fusion_type), ("audio", audio_fusion_type), ("multi", multi_fusion_type)):
+            if ft == "qformer":
+                raise NotImplementedError(f"{name}_fusion_type='qformer' is not built yet (no shipped config uses it)")
+            if ft not in ("attention", "mean"):
+                raise ValueError(f"unknown {name}_fusion_type {ft!r}")
+        if multi_fusion_type != "attention":
+            raise ValueError("multi_fusion_type must be 'attention' (affectgpt.py:910-915)")
+        self.visual_encoder = visual_encoder
+        self.acoustic_encoder = acoustic_encoder
+        self.video_fusion_type = video_fusion_type
+        self.audio_fusion_type = audio_fusion_type
+        self.multi_fusion_type = multi_fusion_type
+        self.num_video_query_token = num_video_query_token
+        self.num_audio_query_token = num_audio_query_token
+        self.num_multi_query_token = num_multi_query_token
+        self.llm_dim = llm_dim
+        self._engine = engine
+        self._engine_cfg = dict(engine_cfg or {})
+        self._engine_cfg.setdefault("llm_dim", llm_dim)
+        self._fusion_state: Optional[Dict[str, torch.Tensor]] = None
+        if engine is not None:
+            for enc in (visual_encoder, acoustic_encoder):
+                if enc is not None and hasattr(enc, "attach_engine"):
+                    enc.attach_engine(engine)
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict, strict: bool = False):   # noqa: D401 - nn.Module signature
+        """Accepts ``ckpt['model']`` (affectgpt.py:1099-1120); only the fusion/projector keys are consumed."""
+        picked = {k: v for k, v in state_dict.items() if k.split(".")[0] in FUSION_KEYS}
+        self._fusion_state = picked
+        if self._engine is not None:
+            self._upload()
+        missing = [f"{k}.{s}" for k in FUSION_KEYS for s in ("weight", "bias") if f"{k}.{s}" not in picked]
+        if strict and missing:
+            raise RuntimeError(f"missing keys: {missing}")
+        return missing, [k for k in state_dict if k not in picked]
+
+    def _upload(self):
+        self._engine.load_state_dict("fusion", self._fusion_state, strict=False)
+        self._fusion_state = None
+
+    def _eng(self, device: torch.device) -> Engine:
+        if self._engine is None:
+            if device.type != "cuda":
+                raise RuntimeError(f"inputs are on {device}; affectgpt_b200 has no CPU fallback")
+            self._engine = get_engine(device, **self._engine_cfg)
+        if self._fusion_state is not None:
+            self._upload()
+        miss = self._engine.missing("fusion")
+        if miss:
+            raise RuntimeError(f"fusion weights not loaded: {miss[:4]} ...")
+        return self._engine
+
+    # ------------------------------------------------------------------ reference surface
+    @torch.no_grad()
+    def encode_video_merge(self, video, raw_video, is_preextracted: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (hiddens [b,t,768], llms [b,n_q,D]).  Pre-extracted: ``video`` is the feature tensor [b,t,768] or [b,768]."""
+        if is_preextracted:
+            hidden = video
+            if hidden.dim() == 2:
+                hidden = hidden.unsqueeze(1)                                   # affectgpt.py:553-558
+            elif hidden.dim() != 3:
+                raise ValueError(f"Unexpected video shape: {video.shape}")
+            bypass = True                                                      # :587-589 (t == 1 skips the attention)
+        else:
+            if self.visual_encoder is None:
+                raise RuntimeError("Visual encoder is None but trying to use real-time mode.")   # :614-615
+            hidden = self.visual_encoder(video, raw_video)
+            bypass = False
+        eng = self._eng(hidden.device)
+        llm = eng.video_fuse(hidden, self.video_fusion_type, bypass_t1=bypass)
+        llm = llm.unsqueeze(1).expand(-1, self.num_video_query_token, -1)
+        return hidden, llm
+
+    @torch.no_grad()
+    def encode_audio_merge(self, audio, raw_audio, is_preextracted: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        if is_preextracted:
+            hidden = audio
+            if hidden.dim() != 3:
+                raise ValueError(f"Unexpected audio shape: {audio.shape}")
+        else:
+            if self.acoustic_encoder is None:
+                raise RuntimeError("Acoustic encoder is None but trying to use real-time mode.")  # :633-634, 695-696
+            hidden = self.acoustic_encoder(audio, raw_audio)
+        eng = self._eng(hidden.device)
+        llm = eng.audio_fuse(hidden, self.audio_fusion_type)
+        llm = llm.unsqueeze(1).expand(-1, self.num_audio_query_token, -1)
+        return hidden, llm
+
+    @torch.no_grad()
+    def encode_multi_merge(self, video_hidden_state, audio_hidden_state) -> Tuple[torch.Tensor, torch.Tensor]:
+        eng = self._eng(video_hidden_state.device)
+        multi, llm = eng.multi_fuse(video_hidden_state, audio_hidden_state)
+        return multi, llm.unsqueeze(1).expand(-1, self.num_multi_query_token, -1)
+
+    @torch.no_grad()
+    def encode_clip_batch(self, samples: dict) -> Dict[str, torch.Tensor]:
+        """Encoder + fusion part of ``AffectGPT.forward`` (affectgpt.py:924-947): returns the per-modality LLM
+        tokens {'frame','face','audio','multi'} [b,n_q,D] plus the hiddens under '<name>_hiddens'."""
+        out: Dict[str, torch.Tensor] = {}
+        fof = samples.get("face_or_frame", "multiface_audio_face_frame_text")
+        if "frames" in samples or "raw_frames" in samples:
+            h, l = self.encode_video_merge(samples.get("frames"), samples.get("raw_frames"),
+                                           is_preextracted=samples.get("frame_preextracted", False))
+            out["frame_hiddens"], out["frame"] = h, l
+        if "faces" in samples or "raw_faces" in samples:
+            h, l = self.encode_video_merge(samples.get("faces"), samples.get("raw_faces"),
+                                           is_preextracted=samples.get("face_preextracted", False))
+            out["face_hiddens"], out["face"] = h, l
+        if "audios" in samples or "raw_audios" in samples:
+            h, l = self.encode_audio_merge(samples.get("audios"), samples.get("raw_audios"),
+                                           is_preextracted=samples.get("audio_preextracted", False))
+            out["audio_hiddens"], out["audio"] = h, l
+        if "audio_hiddens" in out:
+            if fof.startswith("multiface") and "face_hiddens" in out:
+                out["multi_hiddens"], out["multi"] = self.encode_multi_merge(out["face_hiddens"], out["audio_hiddens"])
+            elif fof.startswith("multiframe") and "frame_hiddens" in out:
+                out["multi_hiddens"], out["multi"] = self.encode_multi_merge(out["frame_hiddens"], out["audio_hiddens"])
+        return out
+
+
+def build_path(clip_state: Dict[str, torch.Tensor], hubert_state: Dict[str, torch.Tensor],
+               fusion_state: Dict[str, torch.Tensor], device="cuda:0", vit_layers: int = 24, hubert_layers: int = 24,
+               feat_extract_norm: str = "layer", do_normalize: bool = True, norm_scope: str = "clip",
+               llm_dim: int = config.LLM_DIM, max_frames_per_chunk: int = 512,
+               max_segments_per_chunk: int = 512) -> AffectGPTFusion:
+    """One engine, both encoders and the fusion heads on ``device`` from in-memory state dicts."""
+    eng = Engine(device, vit_layers=vit_layers, hubert_layers=hubert_layers, feat_extract_norm=feat_extract_norm,
+                 do_normalize=do_normalize, llm_dim=llm_dim, max_frames_per_chunk=max_frames_per_chunk,
+                 max_segments_per_chunk=max_segments_per_chunk)
+    vis = CLIP_VIT_LARGE(model_dir="", num_layers=vit_layers)
+    vis.load_hf_state_dict(clip_state)
+    aud = HUBERT_LARGE(model_dir="", num_layers=hubert_layers, feat_extract_norm=feat_extract_norm,
+                       do_normalize=do_normalize, norm_scope=norm_scope)
+    aud.load_hf_state_dict(hubert_state)
+    model = AffectGPTFusion(vis, aud, llm_dim=llm_dim, engine=eng)
+    model.load_state_dict(fusion_state)
+    return model

@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""Headline benchmark: fused clips/sec of the encode-and-fuse path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips B] [--impl ours|reference]
+
+* step      = one pass of the hot path over one batch of B synthetic clips per GPU (config C2: B = 64 clips,
+              each 8 frames 224x224 + 8 x 2 s of 16 kHz audio -> frame / audio / multi tokens at width 3584).
+* value     = clips/s summed over all ranks, inputs already resident in HBM, CUDA-event timed, max over ranks.
+* e2e       = same metric through the reference-facing wrappers with PINNED HOST buffers: H2D of frames and
+              audio, forward, D2H of the fused tokens, all inside the timed region of every step.
+* roofline  = tensor bound: algorithmic FLOPs of the tcgen05 GEMM launches / their summed CUDA-event duration
+              (agb_profile_* event pairs on the launching stream, separate instrumented pass) vs the measured
+              sustained cuBLAS bf16 peak in MEASURED_PEAKS.json.
+* cpu_baseline = the oracle (HF fp32 modules + restated reference wrappers) timed on this box's host cores on a
+              bounded sample (rank 0, N = 1 only).  `--impl reference` times that same CPU path as the arm.
+Multi-GPU: one process per GPU (torchrun), clips sharded across ranks, one NCCL all_gather of the fused tokens.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_VIT_FRAME = 162.026          # SURVEY 8d / BASELINE.md section 3 (2*MAC, dense)
+GF_HUBERT_SEG = 72.35
+GF_FUSE_CLIP = 0.034
+METRIC = "fused clips/sec (8 frames+4 s audio)"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_burst": d.get("bf16_tflops", 1590.0), "bf16_sustained": d.get("bf16_tflops_sustained", 1400.0),
+                "hbm": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_clips_per_sec(n_clips: int, warmup: int = 1):
+    """Oracle (the reference's CPU path restated over HF modules), fp32, all host threads, b = 1 per call as the
+    reference's extractor does (A/extract_multimodal_features_precompute.py:892)."""
+    from oracle import reference_path as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    clip = R.build_clip_vision(24, seed=1234)
+    hub = R.build_hubert(24, "layer", seed=1234)
+    fus = R.build_fusion_state(seed=1234)
+
+    def one(i):
+        fh = R.clip_vit_large_forward(clip, R.synth_frames(1, 8, seed=100 + i))
+        ah = R.hubert_large_forward(hub, R.synth_audio(1, 8, seed=200 + i))
+        return R.fused_tokens(fus, fh, None, ah, "multiframe_audio_frame_text")
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(n_clips):
+        one(warmup + i)
+    dt = time.perf_counter() - t0
+    return n_clips / dt, cores, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = 1
+    vals = []
+    from oracle import reference_path as R  # noqa: F401  (the CPU arm IS the oracle; nothing of ours on this path)
+    cps, cores, _ = cpu_oracle_clips_per_sec(per_step * max(args.steps, 1), warmup=min(args.warmup, 1))
+    vals.append(cps)
+    line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / cps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 clip shape (8 frames 224^2 + 8x2s audio), CPU reference path, batch 1 per call"},
+            "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step * max(args.steps, 1)} clips at batch 1 after {min(args.warmup, 1)} warm-up"},
+            "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step (C2: 64)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import engine as E, parallel as P, synthetic as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    B = args.clips
+
+    model = agb.build_path(S.clip_state(24, dev), S.hubert_state(24, "layer", dev), S.fusion_state(3584, dev), device=dev,
+                           max_frames_per_chunk=512, max_segments_per_chunk=512)
+    # host (pinned) and device copies of this rank's batch; frames fp32 0..255 as the reference passes them
+    h_frames = S.frames(B, 8, seed=1000 + rank).pin_memory()
+    h_audio = S.audio(B, 8, seed=2000 + rank).pin_memory()
+    d_frames, d_audio = h_frames.to(dev), h_audio.to(dev)
+    h_tokens = torch.empty((B, 3, 3584), dtype=torch.float32).pin_memory()
+    total_clips = B * world
+
+    def step(frames, audio):
+        out = model.encode_clip_batch({"raw_frames": frames, "raw_audios": audio, "face_or_frame": "multiframe_audio_frame_text"})
+        toks = torch.cat([out["multi"], out["audio"], out["frame"]], dim=1)          # [B,3,3584]
+        if world > 1:
+            toks = P.gather_clip_rows(toks.contiguous(), total_clips)
+        return toks
+
+    def step_e2e():
+        f = h_frames.to(dev, non_blocking=True)
+        a = h_audio.to(dev, non_blocking=True)
+        toks = step(f, a)
+        h_tokens.copy_(toks[:B] if world > 1 else toks, non_blocking=True)
+        return toks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        step(d_frames, d_audio)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = E.launch_count()
+    ms_dev = timed(lambda: step(d_frames, d_audio), args.steps)
+    launches = E.launch_count() - l0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # instrumented pass: CUDA-event pairs around every kernel wrapper (separate from the timed value)
+    barrier()
+    E.profile_begin()
+    for _ in range(args.steps):
+        step(d_frames, d_audio)
+    prof = E.profile_end()
+
+    value = total_clips * args.steps / (ms_dev / 1e3)
+    e2e_value = total_clips * args.steps / (ms_e2e / 1e3)
+    peaks = read_peaks()
+    g = prof["gemm"]
+    gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
+    tf_per_clip = (8 * GF_VIT_FRAME + 8 * GF_HUBERT_SEG + GF_FUSE_CLIP) / 1e3
+    step_tflops = value / world * tf_per_clip
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"C2: {B} clips/GPU x (8 frames 224^2 + 8x2s 16kHz audio) -> frame/audio/multi tokens @3584",
+                   "clips_per_gpu": B, "weights": "random-init CLIP ViT-L/14 + HuBERT-large (layer-norm conv) + heads",
+                   "cache": "inputs (373 MB/step) and activations exceed the 126 MB L2", "parallelism": f"dp{world}",
+                   "tflop_per_clip": tf_per_clip},
+        "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(h_frames.numel() * 4 + h_audio.numel() * 4), "d2h_bytes_per_step": int(h_tokens.numel() * 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": None, "kernel": "gemm_kernel (tcgen05, all GEMM launches)",
+                     "peak_source": peaks["source"] + ", sustained", "gemm_launches": g["launches"], "gemm_ms_per_step": g["ms"] / args.steps,
+                     "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peaks["bf16_sustained"],
+                     "time_share": {k: v["ms"] / tot_ms for k, v in prof.items()},
+                     "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12) if prof["attention"]["ms"] > 0 else 0.0,
+                     "layernorm_gbs": (prof["layernorm"]["bytes"] / (prof["layernorm"]["ms"] / 1e3) / 1e9) if prof["layernorm"]["ms"] > 0 else 0.0,
+                     "frontend_gbs": (prof["frontend"]["bytes"] / (prof["frontend"]["ms"] / 1e3) / 1e9) if prof["frontend"]["ms"] > 0 else 0.0},
+        "clocks": clk,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cps, cores, dt = cpu_oracle_clips_per_sec(args.cpu_clips, warmup=1)
+        line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_clips} clips at batch 1 (oracle: HF fp32 + restated wrappers), 1 warm-up, {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,13 @@ int agb_set_tap(agb_ctx* ctx, const char* name, void* dst, int64_t capacity_byte
 /* kernels launched by this library since process start (for bench.py's gpu_launches) */
 int64_t agb_launch_count(void);
 
+/* Per-category device timing with CUDA events around every kernel wrapper (roofline legs of bench.py).
+ * Categories: 0 GEMM (tcgen05), 1 attention, 2 LayerNorm, 3 front-end (patchify / conv0 / pooling), 4 other.
+ * `flops` / `bytes` are the ALGORITHMIC counts of the wrapped launches. */
+#define AGB_PROFILE_CATEGORIES 5
+int agb_profile_begin(void);
+int agb_profile_end(double* ms, int64_t* count, double* flops, double* bytes);
+
 /* ---- kernel-level entry points (unit tests, micro-benchmarks) ---------------------------------- */
 /* C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ res); bf16 operands, fp32 accumulate in TMEM.
  * a_mode: 0 plain (lda elements), 1 conv k3/s2 pair view (K = 1536), 2 grouped positional conv. */

@@ -1,0 +1,76 @@
+"""Host-side mirror of the reference interface: registry, wrapper signatures, error behaviour (CPU only)."""
+import inspect
+
+import pytest
+import torch
+
+import affectgpt_b200 as agb
+from affectgpt_b200.registry import Registry, registry
+
+
+def test_registry_keys_and_zero_arg_constructors():
+    # A/my_affectgpt/models/encoder.py:177, 395 register these names; callers do get_*_class(name)()
+    assert registry.get_visual_encoder_class("CLIP_VIT_LARGE") is agb.CLIP_VIT_LARGE
+    assert registry.get_acoustic_encoder_class("HUBERT_LARGE") is agb.HUBERT_LARGE
+    assert registry.get_model_class("affectgpt") is agb.AffectGPTFusion
+    assert registry.get_visual_encoder_class("nope") is None
+    v = registry.get_visual_encoder_class("CLIP_VIT_LARGE")()
+    a = registry.get_acoustic_encoder_class("HUBERT_LARGE")()
+    assert v.hidden_size == 768 and a.hidden_size == 1024          # encoder.py:192, 411
+    assert isinstance(v, torch.nn.Module) and v.to("cpu").eval() is v
+    assert list(v.named_parameters()) == []                         # frozen in the reference; none here
+
+
+def test_duplicate_registration_raises_keyerror():
+    with pytest.raises(KeyError):                                    # registry.py:147-152
+        @Registry.register_visual_encoder("CLIP_VIT_LARGE")
+        class Dup:  # noqa
+            pass
+
+
+def test_forward_signatures_match_reference():
+    assert list(inspect.signature(agb.CLIP_VIT_LARGE.forward).parameters) == ["self", "image", "raw_image"]
+    assert list(inspect.signature(agb.HUBERT_LARGE.forward).parameters) == ["self", "audio", "raw_audio"]
+    sig = inspect.signature(agb.AffectGPTFusion.encode_video_merge)
+    assert list(sig.parameters) == ["self", "video", "raw_video", "is_preextracted"]
+    assert sig.parameters["is_preextracted"].default is False
+    assert list(inspect.signature(agb.AffectGPTFusion.encode_audio_merge).parameters) == ["self", "audio", "raw_audio", "is_preextracted"]
+    assert list(inspect.signature(agb.AffectGPTFusion.encode_multi_merge).parameters) == ["self", "video_hidden_state", "audio_hidden_state"]
+
+
+def test_cpu_inputs_fail_loudly():
+    v = agb.CLIP_VIT_LARGE(model_dir="")
+    with pytest.raises(RuntimeError):
+        v(None, torch.zeros(1, 3, 8, 224, 224))
+    with pytest.raises(ValueError):
+        v(None, torch.zeros(1, 3, 8, 200, 200))
+    a = agb.HUBERT_LARGE(model_dir="")
+    with pytest.raises(RuntimeError):
+        a(None, torch.zeros(1, 8, 1, 32000))
+    with pytest.raises(ValueError):
+        a(None, torch.zeros(1, 8, 1, 16000))
+
+
+def test_model_errors_match_reference():
+    m = agb.AffectGPTFusion(None, None)
+    with pytest.raises(RuntimeError):                                # affectgpt.py:614-615
+        m.encode_video_merge(torch.zeros(1, 3, 8, 224, 224), torch.zeros(1, 3, 8, 224, 224))
+    with pytest.raises(RuntimeError):                                # :695-696
+        m.encode_audio_merge(None, torch.zeros(1, 8, 1, 32000))
+    with pytest.raises(ValueError):                                  # :559-560
+        m.encode_video_merge(torch.zeros(1, 2, 3, 4), None, is_preextracted=True)
+    with pytest.raises(NotImplementedError):
+        agb.AffectGPTFusion(None, None, video_fusion_type="qformer")
+    missing, unexpected = m.load_state_dict({"llama_model.x": torch.zeros(1), "fc_att.weight": torch.zeros(2, 1024)})
+    assert "fc_att.bias" in missing and unexpected == ["llama_model.x"]
+
+
+def test_product_does_not_import_oracle():
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "affectgpt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
