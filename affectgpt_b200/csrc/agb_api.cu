@@ -427,8 +427,9 @@ int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t 
   if (int r = layernorm512_bf16_gelu(src, M, c->h_fp_g, c->h_fp_b, 1e-5f, false, dst, s)) return r;
   GemmArgs g;
   g.A = dst; g.lda = 512; g.W = c->h_fp_w; g.M = (int)M; g.N = 1024; g.K = 512; g.bias = c->h_fp_bias;
-  g.out_f32 = c->h_resid; g.ld_f32 = 1024; g.out_bf16 = c->h_xln; g.ld_bf16 = 1024;
+  g.out_f32 = c->h_resid; g.ld_f32 = 1024;
   if (int r = gemm_bf16(g, s)) return r;
+  if (int r = convert_f32_to_bf16(c->h_resid, c->h_xln, M * 1024, s)) return r;   // pos-conv A operand
   tap(c, "hubert.featproj", c->h_resid, M * 1024 * 4, s);
   // positional conv embedding: resid += GELU(grouped conv(resid))
   g = GemmArgs();

@@ -1,14 +1,25 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+ residual)
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = act(A[M,K] * W[N,K]^T + bias) (+= into fp32 C)
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1      : MMA issuer    (one thread: tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16, fp32 in TMEM)
+//   warp 1      : MMA issuer    (one thread: tcgen05.mma.kind::f16, fp32 accumulators in TMEM)
 //   warp 2      : TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4..11 : epilogue      (tcgen05.ld -> bias / GELU / residual -> 16-byte global stores)
+//   warps 4..11 : epilogue      (tcgen05.ld -> bias / GELU -> swizzled smem staging -> TMA store, or TMA
+//                                reduce-add for the residual stream: the "+= residual" happens in L2, the
+//                                epilogue never reads the residual and issues no LSU global traffic)
 //
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), static tile
-// schedule (tile = blockIdx.x + i * gridDim.x, N fastest so concurrent CTAs share the A row block in L2).
+// schedule (N fastest so concurrently running CTAs share the A row block in L2).
 //
-// A-operand modes (AMode): plain row-major; k=3/s=2 conv as a GEMM over the "pair" view of a
+// CG = 2 (the default for the big GEMMs): two CTAs of a cluster form a pair (tcgen05 cta_group::2).  The pair
+// computes a 256 x BN tile; each CTA stages only its own 128 A rows and HALF of the W tile, the tensor cores
+// read the other half from the peer's shared memory.  Per-SM operand traffic from L2 drops from 48 KB to
+// 32 KB per 64-deep K block ("GEMM roofline").  Protocol (both CTAs run all roles except MMA issue):
+//   full[s]   (leader's copy) : 2 producer arrivals + complete_tx bytes of BOTH CTAs' TMA loads
+//   empty[s]  (every CTA)     : multicast tcgen05.commit from the leader's MMA thread
+//   tfull[a]  (every CTA)     : multicast tcgen05.commit when an accumulator stage is complete
+//   tempty[a] (leader's copy) : epilogue warps of both CTAs arrive remotely
+//
+// A-operand modes (AMode): plain row-major; k=3/s=2 conv as a GEMM over the "pair-of-rows" view of a
 // channels-last activation (no im2col buffer, the third tap is a +1-row TMA coordinate); grouped k=128
 // positional conv (one tap per K block, TMA row coordinate shifted by tap-64, out-of-range rows
 // zero-filled by TMA = the conv's zero padding).
@@ -17,9 +28,7 @@
 // (transformers/models/clip/modeling_clip.py:310-350, models/hubert/modeling_hubert.py:45-231, 262-370).
 #include <cuda.h>
 
-#include <map>
 #include <mutex>
-#include <tuple>
 
 #include "agb_internal.h"
 #include "agb_ptx.cuh"
@@ -28,45 +37,49 @@ namespace agb {
 
 namespace {
 
-constexpr int BM = 128;
+constexpr int BM = 128;               // rows per CTA
 constexpr int BK = 64;
 constexpr int kNumThreads = 384;      // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kStageBufBytes = 4096;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled (TMA store source)
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;            // per CTA: the pair splits W's rows
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiBytes = kNumEpiWarps * kStageBufBytes;
+  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes;
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct KParams {
   int M, N, K;
   int num_kb;
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles;   // m_tiles counts (128 * CG)-row tiles
   const float* bias;
-  const float* res;
-  long long ld_res;
-  float* out_f32;
-  long long ld_f32;
-  bf16* out_bf16;
-  long long ld_bf16;
-  int seq_stride, seq_valid;
+  int has_f32;            // fp32 output through tmF
+  int reduce_f32;         // ... as an L2 reduce-add into the existing fp32 tensor (residual stream)
+  int has_bf16;           // bf16 output through tmH
 };
 
-template <int BN, int MODE, int ACT>
+template <int BN, int MODE, int ACT, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
-  using C = Cfg<BN>;
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmH, const KParams p) {
+  using C = Cfg<BN, CG>;
   constexpr int S = C::kStages;
+  static_assert(CG == 1 || (MODE != A_POSCONV), "the positional-conv mode runs single-CTA");
   extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs of a pair: the peer's operands / barriers live at the same offsets
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + S * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * (C::kABytes + C::kBBytes));
+  uint8_t* smE = smem + S * C::kStageBytes;                       // epilogue staging, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smE + C::kEpiBytes);
   uint64_t* full = bars;            // [S]  TMA -> MMA
   uint64_t* empty = bars + S;       // [S]  MMA -> TMA
   uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
@@ -75,66 +88,86 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.has_f32) tma_prefetch_desc(&tmF);
+    if (p.has_bf16) tma_prefetch_desc(&tmH);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], CG);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kNumEpiWarps);
+      mbar_init(&tempty[i], kNumEpiWarps * CG);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+  if constexpr (CG == 2) cluster_sync_all();   // peer is resident before the paired TMEM allocation
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_slot, C::kTmemCols); else tmem_alloc(tmem_slot, C::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = p.m_tiles * p.n_tiles;
+  const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
-    // ================================================================ TMA producer (one thread)
+    // ================================================================ TMA producer (one thread per CTA)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int row0 = mt * (BM * CG) + (int)cta_rank * BM;          // this CTA's 128 A rows
+        const int wrow0 = nt * BN + (int)cta_rank * (BN / CG);          // this CTA's share of the W tile
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 1);
-          mbar_arrive_expect_tx(&full[stage], C::kABytes + C::kBBytes);
           void* dA = smA + stage * C::kABytes;
           void* dB = smB + stage * C::kBBytes;
-          if constexpr (MODE == A_PLAIN) {
-            tma_load_2d(dA, &tmA, &full[stage], kb * BK, mt * BM, kEvictNormal);
-            tma_load_2d(dB, &tmB, &full[stage], kb * BK, nt * BN, kEvictLast);
-          } else if constexpr (MODE == A_CONV3) {
-            // K blocks 0..15: pair row m, cols kb*64; K blocks 16..23: pair row m+1, cols (kb-16)*64
-            tma_load_2d(dA, &tmA, &full[stage], (kb & 15) * BK, mt * BM + (kb >> 4), kEvictNormal);
-            tma_load_2d(dB, &tmB, &full[stage], kb * BK, nt * BN, kEvictLast);
+          if constexpr (CG == 2) {
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+            if constexpr (MODE == A_PLAIN) {
+              tma_load_2d_pair(dA, &tmA, &full[stage], kb * BK, row0, kEvictNormal);
+            } else {
+              tma_load_2d_pair(dA, &tmA, &full[stage], (kb & 15) * BK, row0 + (kb >> 4), kEvictNormal);
+            }
+            tma_load_2d_pair(dB, &tmB, &full[stage], kb * BK, wrow0, kEvictLast);
+            if (!leader) mbar_arrive_remote(&full[stage], 0);
           } else {
-            // mt = sequence, nt = group; tap kb reads rows t + kb - 64 (TMA zero-fills t outside [0, valid))
-            tma_load_3d(dA, &tmA, &full[stage], nt * 64, kb - 64, mt, kEvictNormal);
-            tma_load_2d(dB, &tmB, &full[stage], kb * BK, nt * BN, kEvictLast);
+            mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+            if constexpr (MODE == A_PLAIN) {
+              tma_load_2d(dA, &tmA, &full[stage], kb * BK, row0, kEvictNormal);
+            } else if constexpr (MODE == A_CONV3) {
+              // K blocks 0..15: pair row m, cols kb*64; K blocks 16..23: pair row m+1, cols (kb-16)*64
+              tma_load_2d(dA, &tmA, &full[stage], (kb & 15) * BK, row0 + (kb >> 4), kEvictNormal);
+            } else {
+              // mt = sequence, nt = group; tap kb reads rows t + kb - 64 (TMA zero-fills t outside [0, valid))
+              tma_load_3d(dA, &tmA, &full[stage], nt * 64, kb - 64, mt, kEvictNormal);
+            }
+            tma_load_2d(dB, &tmB, &full[stage], kb * BK, wrow0, kEvictLast);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+    // ================================================================ MMA issuer (one thread, leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1u, 2);
@@ -148,36 +181,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);                         // smem slot free once these MMAs retire
-          if (kb == p.num_kb - 1) umma_commit(&tfull[as]);    // accumulator complete
+          if constexpr (CG == 2) {
+            umma_commit_pair(&empty[stage], 0x3);                        // smem slot free in both CTAs
+            if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as], 0x3);   // accumulator complete in both CTAs
+          } else {
+            umma_commit(&empty[stage]);
+            if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+      }
+      if constexpr (CG == 2) {
+        // the peer's remote tempty arrivals must have landed before this CTA's shared memory goes away
+        for (int d = 0; d < 2 && d < it; ++d) {
+          const int last = it - 1 - d;
+          mbar_wait(&tempty[last & 1], (last >> 1) & 1, 5);
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ================================================================ epilogue (8 warps)
+    // ================================================================ epilogue (8 warps per CTA)
     const int ew = warp - kEpiWarp0;
     const int q = warp & 3;            // TMEM lane quarter this warp may access (warp id % 4)
     const int half = ew >> 2;          // column half handled by this warp
     constexpr int HC = BN / 2;         // columns per warp
     constexpr int NCH = HC / 32;       // 32-column chunks per warp (1, 2 or 4)
+    uint8_t* stg = smE + ew * kStageBufBytes;            // this warp's staging tile: 32 rows x 128 B
+    uint8_t* my_row = stg + lane * 128;
+    const int sw = lane & 7;                             // 128B swizzle: 16-byte chunk index ^= row % 8
+    bool store_pending = false;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int r_in_tile = q * 32 + lane;
-      long long grow;
-      bool row_ok;
-      if constexpr (MODE == A_POSCONV) {
-        grow = (long long)mt * p.seq_stride + r_in_tile;
-        row_ok = r_in_tile < p.seq_valid;
-      } else {
-        grow = (long long)mt * BM + r_in_tile;
-        row_ok = grow < p.M;
-      }
+      const int row_base = MODE == A_POSCONV ? q * 32 : mt * (BM * CG) + (int)cta_rank * BM + q * 32;
       const int col0 = nt * BN + half * HC;
 
       mbar_wait(&tfull[as], aphase, 4);
@@ -195,62 +238,89 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // all of this warp's accumulator columns are in registers: hand the TMEM stage back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+          }
         }
-        if (row_ok) {
-          const uint32_t* vv = v[c & 1];
-          const int cbase = col0 + c * 32;
+        const int cbase = col0 + c * 32;
+        float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const int col = cbase + j;
-            if (col < p.N) {
-              float x[8];
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[c & 1][j]);
+        if (p.bias != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(vv[j + i]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-              }
-              if constexpr (ACT == ACT_QUICK_GELU) {
+          for (int j = 0; j < 32; j += 4) {
+            if (cbase + j < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+              x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+            }
+          }
+        }
+        if constexpr (ACT == ACT_QUICK_GELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = quick_gelu(x[i]);
-              } else if constexpr (ACT == ACT_GELU_ERF) {
+          for (int j = 0; j < 32; ++j) x[j] = quick_gelu(x[j]);
+        } else if constexpr (ACT == ACT_GELU_ERF) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+          for (int j = 0; j < 32; ++j) x[j] = gelu_erf_fast(x[j]);
+        }
+        if (p.has_f32) {
+          // ---- fp32 tile [32 rows x 32 cols] -> staging -> TMA store / reduce-add
+          if (store_pending) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(my_row + ((j ^ sw) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && cbase < p.N) {
+            if constexpr (MODE == A_POSCONV) {
+              tma_reduce_add_3d(&tmF, stg, cbase, row_base, mt);
+            } else {
+              if (p.reduce_f32) tma_reduce_add_2d(&tmF, stg, cbase, row_base); else tma_store_2d(&tmF, stg, cbase, row_base);
+            }
+            tma_store_commit();
+          }
+          store_pending = true;
+        }
+        if constexpr (HC >= 64) {
+          if (p.has_bf16) {
+            // ---- bf16 tile [32 rows x 64 cols]: two chunks fill the left / right 64 B of each 128 B row
+            if ((c & 1) == 0 && store_pending) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+              store_pending = false;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(x[8 * j], x[8 * j + 1]);
+              o.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+              o.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
+              o.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+              *reinterpret_cast<uint4*>(my_row + ((((c & 1) * 4 + j) ^ sw) << 4)) = o;
+            }
+            if (c & 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0 && cbase - 32 < p.N) {
+                tma_store_2d(&tmH, stg, cbase - 32, row_base);
+                tma_store_commit();
               }
-              if (p.res != nullptr) {
-                const float4* rp = reinterpret_cast<const float4*>(p.res + grow * p.ld_res + col);
-                const float4 r0 = rp[0], r1 = rp[1];
-                x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-                x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-              }
-              if (p.out_f32 != nullptr) {
-                float4* op = reinterpret_cast<float4*>(p.out_f32 + grow * p.ld_f32 + col);
-                op[0] = make_float4(x[0], x[1], x[2], x[3]);
-                op[1] = make_float4(x[4], x[5], x[6], x[7]);
-              }
-              if (p.out_bf16 != nullptr) {
-                uint4 o;
-                o.x = pack_bf16x2(x[0], x[1]);
-                o.y = pack_bf16x2(x[2], x[3]);
-                o.z = pack_bf16x2(x[4], x[5]);
-                o.w = pack_bf16x2(x[6], x[7]);
-                *reinterpret_cast<uint4*>(p.out_bf16 + grow * p.ld_bf16 + col) = o;
-              }
+              store_pending = true;
             }
           }
         }
       }
     }
+    if (store_pending && lane == 0) tma_store_wait_read();   // staging must outlive the last bulk store's read
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -272,18 +342,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rank-2 or rank-3 bf16 tensor, dim0 contiguous; box = {64, box1, 1}; 128B swizzle; OOB -> zeros
-int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              uint32_t box1) {
+// rank-2 or rank-3 tensor, dim0 contiguous; box = {box0, box1, 1} with box0 * elem = 128 B; 128B swizzle; OOB -> zeros
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, uint32_t box0, uint32_t box1) {
   EncodeTiledFn fn = get_encode_fn();
   AGB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
   cuuint64_t gdim[3] = {dims[0], dims[1], rank == 3 ? dims[2] : 1};
   cuuint64_t gstr[2] = {strides_bytes[0], rank == 3 ? strides_bytes[1] : 0};
-  cuuint32_t box[3] = {64, box1, 1};
+  cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return 3;
@@ -302,19 +371,46 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int MODE, int ACT>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& kp, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, MODE, ACT>;
+struct Maps {
+  CUtensorMap a, b, f, h;
+};
+
+template <int BN, int MODE, int ACT, int CG>
+int launch(const Maps& m, const KParams& kp, cudaStream_t stream) {
+  auto kern = gemm_kernel<BN, MODE, ACT, CG>;
+  using C = Cfg<BN, CG>;
   static bool configured = false;
   if (!configured) {
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const int tiles = kp.m_tiles * kp.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kNumThreads, Cfg<BN>::kSmemBytes, stream>>>(tmA, tmB, kp);
+  const int units = num_sms() / CG;                       // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+  const int grid = (tiles < units ? tiles : units) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.f, m.h, kp));
   AGB_CHECK_LAUNCH();
   return 0;
+}
+
+bool use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_GEMM_CTA_GROUP");     // bring-up switch: 1 = single-CTA tiles everywhere
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -326,6 +422,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   AGB_REQUIRE(a.out_f32 != nullptr || a.out_bf16 != nullptr, "gemm: no output");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
               "gemm: operands must be 16-byte aligned");
+  AGB_REQUIRE(a.res == nullptr || a.res == a.out_f32, "gemm: the residual must alias the fp32 output (in-place +=)");
 
   const double rows_eff = a.mode == A_POSCONV ? (double)a.nseq * a.seq_valid : (double)a.M;
   LaunchTimer timer(PROF_GEMM, 2.0 * rows_eff * a.N * a.K,
@@ -334,37 +431,46 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
                     stream);
   KParams kp{};
   kp.M = a.M; kp.N = a.N; kp.K = a.K;
-  kp.bias = a.bias; kp.res = a.res; kp.ld_res = a.ld_res;
-  kp.out_f32 = a.out_f32; kp.ld_f32 = a.ld_f32;
-  kp.out_bf16 = a.out_bf16; kp.ld_bf16 = a.ld_bf16;
-  kp.seq_stride = a.seq_stride; kp.seq_valid = a.seq_valid;
+  kp.bias = a.bias;
+  kp.has_f32 = a.out_f32 != nullptr;
+  kp.reduce_f32 = a.res != nullptr;
+  kp.has_bf16 = a.out_bf16 != nullptr;
   if (a.out_f32) AGB_REQUIRE(a.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0, "gemm: f32 out alignment");
   if (a.out_bf16) AGB_REQUIRE(a.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0, "gemm: bf16 out alignment");
-  if (a.res) AGB_REQUIRE(a.ld_res % 4 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0, "gemm: residual alignment");
   if (a.bias) AGB_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias alignment");
+  AGB_REQUIRE(!(a.out_f32 && a.out_bf16), "gemm: exactly one output (fp32 or bf16)");
 
-  CUtensorMap tmA, tmB;
+  // CTA pairs pay off once there are enough 256-row tiles to fill the machine
+  const bool pairs = use_pairs() && a.mode != A_POSCONV && a.M >= 2048;
+  const int cg = pairs ? 2 : 1;
+
+  Maps m{};
+  const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   if (a.mode == A_PLAIN) {
     AGB_REQUIRE(a.K % BK == 0, "gemm: K must be a multiple of 64");
     AGB_REQUIRE(a.lda >= a.K && (a.lda * 2) % 16 == 0, "gemm: bad lda");
     uint64_t dA[2] = {(uint64_t)a.K, (uint64_t)a.M};
     uint64_t sA[1] = {(uint64_t)a.lda * 2};
-    if (int r = make_tmap(&tmA, a.A, 2, dA, sA, BM)) return r;
+    if (int r = make_tmap(&m.a, BF, a.A, 2, dA, sA, 64, BM)) return r;
     kp.num_kb = a.K / BK;
-    kp.m_tiles = (a.M + BM - 1) / BM;
+    kp.m_tiles = (a.M + BM * cg - 1) / (BM * cg);
   } else if (a.mode == A_CONV3) {
     AGB_REQUIRE(a.K == 1536, "gemm: conv3 mode expects K = 3 * 512");
     uint64_t dA[2] = {1024, (uint64_t)a.M};  // pair rows; row M (third tap of the last row) is OOB -> zeros
     uint64_t sA[1] = {1024 * 2};
-    if (int r = make_tmap(&tmA, a.A, 2, dA, sA, BM)) return r;
+    if (int r = make_tmap(&m.a, BF, a.A, 2, dA, sA, 64, BM)) return r;
     kp.num_kb = 24;
-    kp.m_tiles = (a.M + BM - 1) / BM;
+    kp.m_tiles = (a.M + BM * cg - 1) / (BM * cg);
   } else if (a.mode == A_POSCONV) {
     AGB_REQUIRE(a.N == 1024 && a.K == 8192, "gemm: posconv mode expects N = 1024, K = 128 * 64");
     AGB_REQUIRE(a.nseq > 0 && a.seq_valid > 0 && a.seq_valid <= BM && a.seq_stride >= a.seq_valid, "gemm: posconv seq shape");
+    AGB_REQUIRE(a.out_f32 != nullptr && a.res != nullptr && a.out_bf16 == nullptr && a.ld_f32 == 1024,
+                "gemm: posconv writes resid += gelu(conv) (fp32, row stride 1024)");
     uint64_t dA[3] = {1024, (uint64_t)a.seq_valid, (uint64_t)a.nseq};
     uint64_t sA[2] = {1024 * 2, (uint64_t)a.seq_stride * 1024 * 2};
-    if (int r = make_tmap(&tmA, a.A, 3, dA, sA, BM)) return r;
+    if (int r = make_tmap(&m.a, BF, a.A, 3, dA, sA, 64, BM)) return r;
+    uint64_t sF[2] = {1024 * 4, (uint64_t)a.seq_stride * 1024 * 4};
+    if (int r = make_tmap(&m.f, F32, a.out_f32, 3, dA, sF, 32, 32)) return r;   // rows >= seq_valid are clipped
     kp.num_kb = 128;
     kp.m_tiles = a.nseq;
   } else {
@@ -373,24 +479,33 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
 
   uint64_t dB[2] = {(uint64_t)a.K, (uint64_t)a.N};
   uint64_t sB[1] = {(uint64_t)a.K * 2};
+  uint64_t dC[2] = {(uint64_t)a.N, (uint64_t)a.M};
+  if (a.mode != A_POSCONV && a.out_f32) {
+    uint64_t sF[1] = {(uint64_t)a.ld_f32 * 4};
+    if (int r = make_tmap(&m.f, F32, a.out_f32, 2, dC, sF, 32, 32)) return r;
+  }
+  if (a.out_bf16) {
+    uint64_t sH[1] = {(uint64_t)a.ld_bf16 * 2};
+    if (int r = make_tmap(&m.h, BF, a.out_bf16, 2, dC, sH, 64, 32)) return r;   // 64-column boxes: full 128 B rows
+  }
 
   if (a.mode == A_POSCONV) {
-    if (int r = make_tmap(&tmB, a.W, 2, dB, sB, 64)) return r;
+    if (int r = make_tmap(&m.b, BF, a.W, 2, dB, sB, 64, 64)) return r;
     kp.n_tiles = 16;
     AGB_REQUIRE(a.act == ACT_GELU_ERF, "gemm: posconv epilogue is bias + GELU (+ residual)");
-    return launch<64, A_POSCONV, ACT_GELU_ERF>(tmA, tmB, kp, stream);
+    return launch<64, A_POSCONV, ACT_GELU_ERF, 1>(m, kp, stream);
   }
-  if (int r = make_tmap(&tmB, a.W, 2, dB, sB, 256)) return r;
+  if (int r = make_tmap(&m.b, BF, a.W, 2, dB, sB, 64, 256 / cg)) return r;
   kp.n_tiles = (a.N + 255) / 256;
   if (a.mode == A_CONV3) {
-    if (a.act == ACT_NONE) return launch<256, A_CONV3, ACT_NONE>(tmA, tmB, kp, stream);
-    if (a.act == ACT_GELU_ERF) return launch<256, A_CONV3, ACT_GELU_ERF>(tmA, tmB, kp, stream);
+    if (a.act == ACT_NONE) return pairs ? launch<256, A_CONV3, ACT_NONE, 2>(m, kp, stream) : launch<256, A_CONV3, ACT_NONE, 1>(m, kp, stream);
+    if (a.act == ACT_GELU_ERF) return pairs ? launch<256, A_CONV3, ACT_GELU_ERF, 2>(m, kp, stream) : launch<256, A_CONV3, ACT_GELU_ERF, 1>(m, kp, stream);
     AGB_REQUIRE(false, "gemm: unsupported activation for conv3 mode");
   }
   switch (a.act) {
-    case ACT_NONE: return launch<256, A_PLAIN, ACT_NONE>(tmA, tmB, kp, stream);
-    case ACT_QUICK_GELU: return launch<256, A_PLAIN, ACT_QUICK_GELU>(tmA, tmB, kp, stream);
-    case ACT_GELU_ERF: return launch<256, A_PLAIN, ACT_GELU_ERF>(tmA, tmB, kp, stream);
+    case ACT_NONE: return pairs ? launch<256, A_PLAIN, ACT_NONE, 2>(m, kp, stream) : launch<256, A_PLAIN, ACT_NONE, 1>(m, kp, stream);
+    case ACT_QUICK_GELU: return pairs ? launch<256, A_PLAIN, ACT_QUICK_GELU, 2>(m, kp, stream) : launch<256, A_PLAIN, ACT_QUICK_GELU, 1>(m, kp, stream);
+    case ACT_GELU_ERF: return pairs ? launch<256, A_PLAIN, ACT_GELU_ERF, 2>(m, kp, stream) : launch<256, A_PLAIN, ACT_GELU_ERF, 1>(m, kp, stream);
     default: break;
   }
   AGB_REQUIRE(false, "gemm: unknown activation");

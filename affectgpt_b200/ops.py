@@ -35,13 +35,21 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K and a.stride(1) == 1 and w.is_contiguous()
-    of = torch.empty((M, N), dtype=torch.float32, device=a.device) if (out_f32 or res is not None) else None
-    ob = torch.empty((M, N), dtype=torch.bfloat16, device=a.device) if out_bf16 else None
-    if res is not None:
-        assert res.dtype == torch.float32 and res.shape == (M, N) and res.is_contiguous()
+    of = ob = None
+    lib = _lib.load()
     with torch.cuda.device(a.device):
-        _chk(_lib.load().agb_op_gemm(A_PLAIN, ACT[act], _p(a), a.stride(0), _p(w), M, N, K, _p(bias), _p(res), N,
-                                     _p(of), N, _p(ob), N, 0, 0, 0, _s(a)), "agb_op_gemm")
+        if out_f32 or res is not None:       # one output per launch: the fp32 result (optionally += into a copy of res)
+            if res is not None:
+                assert res.dtype == torch.float32 and res.shape == (M, N)
+                of = res.clone().contiguous()
+            else:
+                of = torch.empty((M, N), dtype=torch.float32, device=a.device)
+            _chk(lib.agb_op_gemm(A_PLAIN, ACT[act], _p(a), a.stride(0), _p(w), M, N, K, _p(bias),
+                                 _p(of) if res is not None else None, N, _p(of), N, None, 0, 0, 0, 0, _s(a)), "agb_op_gemm")
+        if out_bf16 and res is None:
+            ob = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+            _chk(lib.agb_op_gemm(A_PLAIN, ACT[act], _p(a), a.stride(0), _p(w), M, N, K, _p(bias), None, 0, None, 0,
+                                 _p(ob), N, 0, 0, 0, _s(a)), "agb_op_gemm")
     return of, ob
 
 

@@ -18,7 +18,8 @@ def _rand(shape, seed, scale=1.0, dtype=torch.float32):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 128), (514, 3072, 1024), (514, 1024, 4096), (200, 768, 1024),
-                                   (1028, 4096, 1024), (8, 256, 64), (257 * 8, 1024, 1024), (512, 1024, 640)])
+                                   (1028, 4096, 1024), (8, 256, 64), (257 * 8, 1024, 1024), (512, 1024, 640),
+                                   (4096, 3072, 1024), (2300, 1024, 4096), (5000, 768, 1024), (2049, 512, 1536)])
 def test_gemm_plain_bias_shapes(M, N, K):
     from affectgpt_b200 import ops
     a = _rand((M, K), 1, 1.0, torch.bfloat16)
@@ -34,7 +35,7 @@ def test_gemm_plain_bias_shapes(M, N, K):
 @pytest.mark.parametrize("act", ["quick_gelu", "gelu"])
 def test_gemm_activation_epilogues(act):
     from affectgpt_b200 import ops
-    M, N, K = 514, 4096, 1024
+    M, N, K = 2570, 4096, 1024
     a = _rand((M, K), 4, 1.0, torch.bfloat16)
     w = _rand((N, K), 5, 2.0 / math.sqrt(K), torch.bfloat16)
     bias = _rand((N,), 6)
@@ -46,7 +47,7 @@ def test_gemm_activation_epilogues(act):
 
 def test_gemm_inplace_residual_and_no_bias():
     from affectgpt_b200 import ops
-    M, N, K = 771, 1024, 1024
+    M, N, K = 2313, 1024, 1024
     a = _rand((M, K), 7, 1.0, torch.bfloat16)
     w = _rand((N, K), 8, 1.0 / math.sqrt(K), torch.bfloat16)
     bias = _rand((N,), 9)

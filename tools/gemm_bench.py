@@ -1,0 +1,48 @@
+"""Micro-benchmark of the tcgen05 GEMM on the path's shapes (CUDA events, L2 flushed between iterations by cycling
+through operand sets larger than the 126 MB L2).  AGB_GEMM_CTA_GROUP=1 forces single-CTA tiles."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from affectgpt_b200 import _lib, ops  # noqa: E402
+
+dev = "cuda:0"
+shapes = [("vit_qkv", 131584, 3072, 1024, None, False), ("vit_out", 131584, 1024, 1024, None, True),
+          ("vit_fc1", 131584, 4096, 1024, "quick_gelu", False), ("vit_fc2", 131584, 1024, 4096, None, True),
+          ("hub_qkv", 51200, 3072, 1024, None, False), ("hub_ffn1", 51200, 4096, 1024, "gelu", False),
+          ("hub_ffn2", 51200, 1024, 4096, None, True), ("patch", 131072, 1024, 640, None, False)]
+res = {}
+lib = _lib.load()
+for name, M, N, K, act, resid in shapes:
+    a = torch.randn(M, K, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=dev) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    r = torch.randn(M, N, device=dev) if resid else None
+    ob = None if resid else torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    s = int(torch.cuda.current_stream().cuda_stream)
+
+    def run():
+        rc = lib.agb_op_gemm(0, ops.ACT[act], a.data_ptr(), K, w.data_ptr(), M, N, K, bias.data_ptr(),
+                             r.data_ptr() if resid else None, N, r.data_ptr() if resid else None, N,
+                             None if resid else ob.data_ptr(), N, 0, 0, 0, s)
+        assert rc == 0, _lib.last_error()
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 20
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    res[name] = {"ms": ms, "tflops": tf}
+    print(f"{name:9s} M={M} N={N} K={K}: {ms:.3f} ms  {tf:.0f} TFLOP/s", flush=True)
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+os.makedirs(out, exist_ok=True)
+json.dump(res, open(os.path.join(out, f"gemm_bench_cg{os.environ.get('AGB_GEMM_CTA_GROUP', '2')}.json"), "w"), indent=1)

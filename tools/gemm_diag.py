@@ -15,7 +15,7 @@ os.makedirs(OUT, exist_ok=True)
 dev = "cuda:0"
 res, dump = [], {}
 g = torch.Generator().manual_seed(0)
-for (M, N, K) in [(128, 256, 64), (128, 256, 128), (128, 256, 1024), (256, 512, 64), (100, 64, 64), (300, 768, 256)]:
+for (M, N, K) in [(128, 256, 64), (128, 256, 128), (128, 256, 1024), (256, 512, 64), (100, 64, 64), (300, 768, 256), (2048, 256, 64), (2056, 512, 128), (4096, 768, 1024)]:
     a = torch.randint(-2, 3, (M, K), generator=g).to(torch.bfloat16).to(dev)
     w = torch.randint(-2, 3, (N, K), generator=g).to(torch.bfloat16).to(dev)
     try:
