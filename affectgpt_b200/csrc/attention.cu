@@ -194,6 +194,15 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
               "attention: alignment");
   LaunchTimer timer(PROF_ATTENTION, 4.0 * nseq * 16.0 * (double)seq_valid * seq_valid * 64.0,
                     (double)nseq * seq_valid * 4096.0 * 2.0, s);
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("AGB_ATTENTION");          // bring-up switch: "hmma" forces the mma.sync kernel
+    legacy = (e != nullptr && e[0] == 'h') ? 1 : 0;
+  }
+  if (!legacy) {
+    const int r = attention_tc(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+    if (r >= 0) return r;
+  }
   if (seq_valid <= 112) return launch_mha<7>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   if (seq_valid <= 272) return launch_mha<17>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   AGB_REQUIRE(false, "attention: sequence length > 272 not supported by the register-resident softmax kernel");

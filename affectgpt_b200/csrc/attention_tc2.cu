@@ -1,0 +1,503 @@
+// tcgen05 multi-head attention, second generation: two co-resident CTAs per SM, eight softmax warps per CTA.
+//
+// Shapes on the path: ViT 257 tokens (16 heads x 64) and HuBERT 99 frames; non-causal, K/V of a head fit in smem.
+// The kernel is bound by the exponentials (MUFU: 16/clk/SM -> 257^2/16 = 4128 clk per (frame, head) against 2064 clk of
+// tensor work), so the structure is chosen to keep the MUFU pipe of every SM sub-partition fed:
+//
+//   * TMEM budget 256 columns per CTA -> 2 CTAs per SM; while one CTA's tensor work runs the other one exponentiates.
+//   * softmax group A (warps 4-7) and group B (warps 8-11) split the key columns of the same 128 query rows
+//     (a warp may only touch TMEM lanes 32*(warp%4)..+31, so A/B warps with the same warp%4 share rows);
+//     row max and row sum are exchanged through shared memory.
+//   * 257 = 2*128 + 1.  The odd KEY is a 16-row "stray" block: its scores S_C = Q K_C^T (N = 16) are produced one tile
+//     ahead into spare TMEM columns and held in a register, its probability goes through one extra K=16 PV step.
+//     The odd QUERY is a third tile whose single valid row is rotated over the four lane quarters (tile start row
+//     256 - 32*(j%4)) so that the extra softmax work is spread over the four SM sub-partitions; warps without a
+//     valid row skip the math.
+//
+//   warp 0 : TMA producer (K, V single-buffered per head; Q ring of 2)       warp 1 : tcgen05.mma issuer
+//   warp 2 : TMEM allocator                                                   warps 4-11 : softmax + epilogue
+//
+// TMEM columns (ViT, NMAIN = 256):  S [0,256)  ->  P_A [0,64) | O [64,128) | P_B [128,192) | P_C [192,200) | S_C(next) [208,224)
+//              (HuBERT, NMAIN = 112): S [0,112) ->  P_A [0,32) | P_B [64,88) ;  O [128,192)
+// P (bf16 pairs) overwrites the first half of the S columns its own group has already consumed; O reuses the second
+// half of group A's S columns, which are dead once P_A is complete.
+//
+// Exact softmax: global row max (fp32) before the first exponential, exp2 with the scale folded in, fp32 row sum of
+// the unrounded probabilities, P rounded to bf16 for the PV product (same as every flash-attention implementation).
+//
+// Replaces CLIPAttention.forward (HF modeling_clip.py:262-332, scale 1/8, fp32 softmax) and
+// HubertAttention.forward (HF modeling_hubert.py:262-370).
+#include <cuda.h>
+
+#include "agb_internal.h"
+#include "agb_ptx.cuh"
+
+namespace agb {
+
+int make_tmap_generic(CUtensorMap* out, int dtype_is_f32, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, uint32_t box0, uint32_t box1);
+
+namespace {
+
+constexpr int kThreads = 384;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// barrier 1: the 256 softmax threads only (warps 4-11)
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// V tile [keys][64 d] as the B operand of P.V: N (= d) contiguous -> MN-major, 128B swizzle, 8-key groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t m, uint32_t n, uint32_t b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+struct AParams {
+  int nseq, seq_stride, seq_valid, qtiles;
+  float scale_log2e;
+  bf16* out;
+};
+
+template <int NMAIN, bool STRAY>
+struct Cfg {
+  static constexpr int CA = NMAIN == 256 ? 128 : 64;       // key columns of softmax group A
+  static constexpr int CB = NMAIN - CA;                     // ... of group B
+  static constexpr int NKROWS = NMAIN + (STRAY ? 16 : 0);   // K / V rows staged per head
+  static constexpr int kKVBytes = NKROWS * 128;
+  static constexpr int kQBytes = 128 * 128;
+  static constexpr int kColPA = 0, kColPB = CA;
+  static constexpr int kColO = NMAIN == 256 ? 64 : 128;
+  static constexpr int kColPC = 192, kColSC = 208;
+  static constexpr int kTmemCols = 256;
+  static constexpr int kOffV = kKVBytes, kOffQ = 2 * kKVBytes, kOffX = kOffQ + 2 * kQBytes, kOffBar = kOffX + 2048;
+  static constexpr int kSmem = kOffBar + 256 + 1024;        // + alignment slack
+  static_assert(kKVBytes % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
+  static_assert(CA % 32 == 0 && CB % 16 == 0, "column split");
+};
+
+// ---- softmax pass 1 over W (32 or 16) score columns: running max, optionally masked to keys < valid
+template <int W>
+__device__ __forceinline__ float chunk_max(uint32_t taddr, int key0, int valid, float m) {
+  uint32_t v[W];
+  if (W == 32) tmem_ld_x32(taddr, v); else tmem_ld_x16(taddr, v);
+  tmem_ld_wait();
+  if (key0 + W <= valid) {
+#pragma unroll
+    for (int j = 0; j < W; j += 2) m = fmaxf(m, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; ++j) m = (key0 + j < valid) ? fmaxf(m, __uint_as_float(v[j])) : m;
+  }
+  return m;
+}
+// ---- softmax pass 2: p = exp2(s*sc - mo), row-sum, bf16 pairs stored at p_addr (W/2 columns)
+template <int W>
+__device__ __forceinline__ float chunk_exp(uint32_t s_addr, uint32_t p_addr, int key0, int valid, float sc, float mo,
+                                           float l) {
+  uint32_t v[W];
+  if (W == 32) tmem_ld_x32(s_addr, v); else tmem_ld_x16(s_addr, v);
+  tmem_ld_wait();
+  float l1 = 0.f;
+  if (key0 + W <= valid) {
+#pragma unroll
+    for (int j = 0; j < W; j += 2) {
+      const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mo));
+      const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sc, -mo));
+      l += p0;
+      l1 += p1;
+      v[j >> 1] = pack_bf16x2(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < W; j += 2) {
+      float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mo));
+      float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sc, -mo));
+      p0 = (key0 + j < valid) ? p0 : 0.f;
+      p1 = (key0 + j + 1 < valid) ? p1 : 0.f;
+      l += p0;
+      l1 += p1;
+      v[j >> 1] = pack_bf16x2(p0, p1);
+    }
+  }
+  if (W == 32) tmem_st_x16(p_addr, v); else tmem_st_x8(p_addr, v);
+  return l + l1;
+}
+
+template <int NMAIN, bool STRAY>
+__global__ void __launch_bounds__(kThreads, 2)
+mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+               const __grid_constant__ CUtensorMap tmStray, const AParams p) {
+  using C = Cfg<NMAIN, STRAY>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smK = smem;
+  uint8_t* smV = smem + C::kOffV;
+  uint8_t* smQ = smem + C::kOffQ;
+  float* xm = reinterpret_cast<float*>(smem + C::kOffX);   // [2 groups][128 rows] partial row max
+  float* xl = xm + 256;                                    // [2][128] partial row sum
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
+  uint64_t* k_full = bars + 0;
+  uint64_t* k_empty = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* v_empty = bars + 3;
+  uint64_t* q_full = bars + 4;     // [2]
+  uint64_t* q_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* sc_full = bars + 9;
+  uint64_t* sc_read = bars + 10;   // 8 warps
+  uint64_t* pa_ready = bars + 11;  // 4 warps
+  uint64_t* pb_ready = bars + 12;  // 4 warps
+  uint64_t* o_full = bars + 13;
+  uint64_t* o_read = bars + 14;    // 8 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    if (STRAY) tma_prefetch_desc(&tmStray);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
+    mbar_init(s_full, 1); mbar_init(sc_full, 1); mbar_init(sc_read, 8);
+    mbar_init(pa_ready, 4); mbar_init(pb_ready, 4);
+    mbar_init(o_full, 1); mbar_init(o_read, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_items = p.nseq * 16;
+  const int QT = p.qtiles;
+  const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int T = my_items * QT;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int t = 0;
+      for (int j = 0; j < my_items; ++j) {
+        const int item = blockIdx.x + j * gridDim.x;
+        const int seq = item >> 4, head = item & 15;
+        const int r0 = 32 * (j & 3);
+        mbar_wait(k_empty, (j & 1) ^ 1u, 21);
+        mbar_arrive_expect_tx(k_full, C::kKVBytes);
+        tma_load_3d(smK, &tmKV, k_full, 1024 + head * 64, 0, seq, kEvictNormal);
+        if (STRAY) tma_load_3d(smK + NMAIN * 128, &tmStray, k_full, 1024 + head * 64, NMAIN, seq, kEvictNormal);
+        for (int qt = 0; qt < QT; ++qt, ++t) {
+          const int qs = t & 1;
+          mbar_wait(&q_empty[qs], ((t >> 1) & 1) ^ 1u, 22);
+          mbar_arrive_expect_tx(&q_full[qs], C::kQBytes);
+          tma_load_3d(smQ + qs * C::kQBytes, &tmQ, &q_full[qs], head * 64, qt < 2 ? qt * 128 : 256 - r0, seq,
+                      kEvictFirst);
+          if (qt == 0) {
+            mbar_wait(v_empty, (j & 1) ^ 1u, 23);
+            mbar_arrive_expect_tx(v_full, C::kKVBytes);
+            tma_load_3d(smV, &tmKV, v_full, 2048 + head * 64, 0, seq, kEvictNormal);
+            if (STRAY) tma_load_3d(smV + NMAIN * 128, &tmStray, v_full, 2048 + head * 64, NMAIN, seq, kEvictNormal);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0 && T > 0) {
+      constexpr uint32_t idS = idesc_bf16(128, NMAIN, 0);
+      constexpr uint32_t idSC = idesc_bf16(128, 16, 0);
+      constexpr uint32_t idO = idesc_bf16(128, 64, 1);
+      const uint64_t dK = umma_desc_kmajor_sw128(smem_u32(smK));
+      const uint64_t dKC = umma_desc_kmajor_sw128(smem_u32(smK + NMAIN * 128));
+      const uint64_t dV = umma_desc_mnmajor_sw128(smem_u32(smV));
+      const uint64_t dQ0 = umma_desc_kmajor_sw128(smem_u32(smQ));
+      const uint64_t dQ1 = umma_desc_kmajor_sw128(smem_u32(smQ + C::kQBytes));
+      auto issue_qk_stray = [&](int t) {
+        const uint64_t da = (t & 1) ? dQ1 : dQ0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + C::kColSC, da + 2 * k, dKC + 2 * k, idSC, k != 0);
+        umma_commit(sc_full);
+      };
+      if (STRAY) {
+        mbar_wait(k_full, 0, 24);
+        mbar_wait(&q_full[0], 0, 25);
+        tc_fence_after();
+        issue_qk_stray(0);
+      }
+      int t = 0;
+      for (int j = 0; j < my_items; ++j) {
+        for (int qt = 0; qt < QT; ++qt, ++t) {
+          const uint32_t ph = t & 1;
+          const bool first = qt == 0, last = qt == QT - 1;
+          if (!STRAY) {
+            if (first) mbar_wait(k_full, j & 1, 24);
+            mbar_wait(&q_full[t & 1], (t >> 1) & 1, 25);
+          }
+          if (t > 0) mbar_wait(o_read, ph ^ 1u, 26);            // epilogue of tile t-1 has drained TMEM
+          if (STRAY) mbar_wait(sc_read, ph, 27);                // S_C(t) is in registers
+          tc_fence_after();
+          {
+            const uint64_t da = (t & 1) ? dQ1 : dQ0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, da + 2 * k, dK + 2 * k, idS, k != 0);
+          }
+          umma_commit(s_full);
+          umma_commit(&q_empty[t & 1]);
+          if (last) umma_commit(k_empty);
+          if (first) mbar_wait(v_full, j & 1, 28);
+          mbar_wait(pa_ready, ph, 29);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < C::CA / 16; ++k)
+            umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPA + 8 * k, dV + 128 * k, idO, k != 0);
+          mbar_wait(pb_ready, ph, 30);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < C::CB / 16; ++k)
+            umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPB + 8 * k, dV + 128 * (C::CA / 16 + k), idO, 1u);
+          if (STRAY) umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPC, dV + 128 * (NMAIN / 16), idO, 1u);
+          umma_commit(o_full);
+          if (last) umma_commit(v_empty);
+          if (STRAY && t + 1 < T) {                               // stray-key scores of the next tile, one tile ahead
+            if (last) mbar_wait(k_full, (j + 1) & 1, 24);
+            mbar_wait(&q_full[(t + 1) & 1], ((t + 1) >> 1) & 1, 25);
+            tc_fence_after();
+            issue_qk_stray(t + 1);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ softmax + epilogue (8 warps)
+    const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;                      // 0 = A (low key columns), 1 = B
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (uint32_t(q * 32) << 16);
+    const int valid = p.seq_valid;
+    const float sc = p.scale_log2e;
+    const bool stray_key = STRAY && valid > NMAIN;
+    float sc_cur = 0.f, sc_next = 0.f;
+    if (STRAY && T > 0) {
+      mbar_wait(sc_full, 0, 31);
+      tc_fence_after();
+      sc_cur = __uint_as_float(tmem_ld_x1(lane_base + C::kColSC));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sc_read);
+    }
+    int t = 0;
+    for (int j = 0; j < my_items; ++j) {
+      const int item = blockIdx.x + j * gridDim.x;
+      const int seq = item >> 4, head = item & 15;
+      const int r0 = 32 * (j & 3);
+      for (int qt = 0; qt < QT; ++qt, ++t) {
+        const uint32_t ph = t & 1;
+        const int grow = (qt < 2 ? qt * 128 : 256 - r0) + row_in_tile;
+        const bool mine = grow < valid && (qt < 2 || row_in_tile >= r0);
+        const bool active = __any_sync(0xffffffffu, mine);
+        mbar_wait(s_full, ph, 32);
+        tc_fence_after();
+        // ---------------- pass 1: row max over this group's key columns
+        float m = -INFINITY;
+        if (active) {
+          if (grp == 0) {
+#pragma unroll
+            for (int c = 0; c < C::CA / 32; ++c) m = chunk_max<32>(lane_base + c * 32, c * 32, valid, m);
+            if (stray_key) m = fmaxf(m, sc_cur);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::CB / 32; ++c) m = chunk_max<32>(lane_base + C::CA + c * 32, C::CA + c * 32, valid, m);
+            if (C::CB % 32) m = chunk_max<16>(lane_base + C::CA + (C::CB / 32) * 32, C::CA + (C::CB / 32) * 32, valid, m);
+          }
+        }
+        xm[grp * 128 + row_in_tile] = m;
+        softmax_bar_sync();
+        m = fmaxf(m, xm[(grp ^ 1) * 128 + row_in_tile]);
+        const float mo = m * sc;
+        // ---------------- pass 2: exponentials, row sum, P (bf16) written over the consumed S columns
+        float l = 0.f;
+        if (active) {
+          if (grp == 0) {
+#pragma unroll
+            for (int c = 0; c < C::CA / 32; ++c)
+              l = chunk_exp<32>(lane_base + c * 32, lane_base + C::kColPA + c * 16, c * 32, valid, sc, mo, l);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::CB / 32; ++c)
+              l = chunk_exp<32>(lane_base + C::CA + c * 32, lane_base + C::kColPB + c * 16, C::CA + c * 32, valid, sc, mo, l);
+            if (C::CB % 32)
+              l = chunk_exp<16>(lane_base + C::CA + (C::CB / 32) * 32, lane_base + C::kColPB + (C::CB / 32) * 16,
+                                C::CA + (C::CB / 32) * 32, valid, sc, mo, l);
+            if (STRAY) {
+              uint32_t pc[8];
+              const float pz = stray_key ? ex2_approx(fmaf(sc_cur, sc, -mo)) : 0.f;
+              l += pz;
+              pc[0] = pack_bf16x2(pz, 0.f);
+#pragma unroll
+              for (int i = 1; i < 8; ++i) pc[i] = 0u;
+              tmem_st_x8(lane_base + C::kColPC, pc);
+            }
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(grp == 0 ? pa_ready : pb_ready);
+        xl[grp * 128 + row_in_tile] = l;
+        if (STRAY && t + 1 < T) {                     // pick up the next tile's stray-key score while P.V runs
+          mbar_wait(sc_full, ph ^ 1u, 33);
+          tc_fence_after();
+          sc_next = __uint_as_float(tmem_ld_x1(lane_base + C::kColSC));
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sc_read);
+        }
+        // ---------------- epilogue: O / l -> bf16 -> global; each group writes 32 of the 64 head channels
+        mbar_wait(o_full, ph, 34);
+        tc_fence_after();
+        softmax_bar_sync();
+        l += xl[(grp ^ 1) * 128 + row_in_tile];
+        uint32_t o[32];
+        if (active) {
+          tmem_ld_x32(lane_base + C::kColO + grp * 32, o);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_read);
+        if (mine) {
+          const float inv = 1.0f / l;
+          bf16* dst = p.out + ((long long)seq * p.seq_stride + grow) * 1024 + head * 64 + grp * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + i) = w;
+          }
+        }
+        sc_cur = sc_next;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int NMAIN, bool STRAY>
+int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s) {
+  using C = Cfg<NMAIN, STRAY>;
+  auto kern = mha_tc2_kernel<NMAIN, STRAY>;
+  static bool configured = false;
+  if (!configured) {
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+    configured = true;
+  }
+  // one 3-D view of the packed QKV activation: {3072 channels, seq_valid rows, nseq}; rows >= seq_valid read as zero
+  uint64_t dims[3] = {3072, (uint64_t)seq_valid, (uint64_t)nseq};
+  uint64_t strides[2] = {3072 * 2, (uint64_t)seq_stride * 3072 * 2};
+  CUtensorMap tq, tkv, tst;
+  if (int r = make_tmap_generic(&tq, 0, qkv, 3, dims, strides, 64, 128)) return r;
+  if (int r = make_tmap_generic(&tkv, 0, qkv, 3, dims, strides, 64, NMAIN)) return r;
+  if (int r = make_tmap_generic(&tst, 0, qkv, 3, dims, strides, 64, 16)) return r;
+  AParams p{};
+  p.nseq = nseq; p.seq_stride = seq_stride; p.seq_valid = seq_valid;
+  p.qtiles = (seq_valid + 127) / 128;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = out;
+  const int items = nseq * 16;
+  const int resident = sm_count() * 2;
+  const int grid = items < resident ? items : resident;
+  kern<<<grid, kThreads, C::kSmem, s>>>(tq, tkv, tst, p);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+// returns -1 when the shape is not covered by an instantiation (caller falls back)
+int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s) {
+  if (seq_valid <= 112) return launch_tc2<112, false>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+  if (seq_valid > 128 && seq_valid <= 257) return launch_tc2<256, true>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+  return -1;
+}
+
+}  // namespace agb

@@ -415,6 +415,12 @@ bool use_pairs() {
 
 }  // namespace
 
+int make_tmap_generic(CUtensorMap* out, int dtype_is_f32, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, uint32_t box0, uint32_t box1) {
+  return make_tmap(out, dtype_is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims,
+                   strides_bytes, box0, box1);
+}
+
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   AGB_REQUIRE(a.A != nullptr && a.W != nullptr, "gemm: null operand");
   AGB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");

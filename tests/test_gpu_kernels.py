@@ -134,7 +134,8 @@ def test_layernorm512_bf16(gelu):
     assert rel_err(got, want) < 6e-3
 
 
-@pytest.mark.parametrize("nseq,stride,valid", [(3, 257, 257), (5, 100, 99), (2, 16, 16), (2, 40, 33), (1, 272, 272)])
+@pytest.mark.parametrize("nseq,stride,valid", [(3, 257, 257), (5, 100, 99), (2, 16, 16), (2, 40, 33), (1, 272, 272),
+                                               (4, 130, 120), (24, 257, 257), (45, 100, 99), (2, 150, 129)])
 def test_attention_vs_sdpa(nseq, stride, valid):
     from affectgpt_b200 import ops
     qkv = _rand((nseq * stride, 3072), 28, 1.0, torch.bfloat16)
