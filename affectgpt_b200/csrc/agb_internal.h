@@ -99,6 +99,8 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
 
 // attention_tc.cu: tcgen05 path; returns -1 when no instantiation covers the shape
 int attention_tc(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s);
+// attention_tc2.cu: two CTAs per SM, eight softmax warps per CTA; same contract
+int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s);
 
 // vit.cu -------------------------------------------------------------------------------------
 int vit_patchify(const void* frames, int in_dtype /*0=f32 0..255, 1=u8*/, int64_t nframes, bf16* a_patch /*[n*256,640]*/,

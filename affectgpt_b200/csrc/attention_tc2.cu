@@ -417,26 +417,30 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
         softmax_bar_sync();
         l += xl[(grp ^ 1) * 128 + row_in_tile];
-        uint32_t o[32];
         if (active) {
+          uint32_t o[32];
           tmem_ld_x32(lane_base + C::kColO + grp * 32, o);
           tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_read);
-        if (mine) {
-          const float inv = 1.0f / l;
-          bf16* dst = p.out + ((long long)seq * p.seq_stride + grow) * 1024 + head * 64 + grp * 32;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_read);
+          if (mine) {
+            const float inv = 1.0f / l;
+            bf16* dst = p.out + ((long long)seq * p.seq_stride + grow) * 1024 + head * 64 + grp * 32;
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-            w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-            w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-            w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + i) = w;
+            for (int i = 0; i < 32; i += 8) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+              w.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+              w.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+              w.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + i) = w;
+            }
           }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_read);
         }
         sc_cur = sc_next;
       }

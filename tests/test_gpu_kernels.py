@@ -135,7 +135,8 @@ def test_layernorm512_bf16(gelu):
 
 
 @pytest.mark.parametrize("nseq,stride,valid", [(3, 257, 257), (5, 100, 99), (2, 16, 16), (2, 40, 33), (1, 272, 272),
-                                               (4, 130, 120), (24, 257, 257), (45, 100, 99), (2, 150, 129)])
+                                               (4, 130, 120), (24, 257, 257), (45, 100, 99), (2, 150, 129), (80, 257, 257),
+                                               (3, 260, 256), (100, 100, 99), (2, 112, 112)])
 def test_attention_vs_sdpa(nseq, stride, valid):
     from affectgpt_b200 import ops
     qkv = _rand((nseq * stride, 3072), 28, 1.0, torch.bfloat16)
@@ -144,6 +145,24 @@ def test_attention_vs_sdpa(nseq, stride, valid):
     q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     want = F.scaled_dot_product_attention(q, k, v, scale=0.125).permute(0, 2, 1, 3)
     assert rel_err(got, want) < 1e-2
+
+
+@pytest.mark.parametrize("nseq,stride,valid", [(20, 257, 257), (40, 100, 99)])
+def test_attention_peaked_rows(nseq, stride, valid):
+    """Large logits (|s| up to ~40) and one dominant key per row: the row-max subtraction and the stray 257th key
+    / 257th query handling must hold when a single probability carries the row."""
+    from affectgpt_b200 import ops
+    qkv = _rand((nseq * stride, 3072), 31, 1.0, torch.bfloat16)
+    qkv[:, :1024] *= 6.0
+    x = qkv.float().reshape(nseq, stride, 3, 16, 64)
+    x[:, valid - 1, 1] = x[:, 0, 0] * 0.5            # last key aligned with query 0 of every head
+    qkv = x.reshape(nseq * stride, 3072).to(torch.bfloat16).contiguous()
+    got = ops.attention(qkv, nseq, stride, valid).float().reshape(nseq, stride, 16, 64)[:, :valid]
+    x = qkv.float().reshape(nseq, stride, 3, 16, 64)[:, :valid]
+    q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    want = F.scaled_dot_product_attention(q, k, v, scale=0.125).permute(0, 2, 1, 3)
+    assert torch.isfinite(got).all()
+    assert rel_err(got, want) < 1.5e-2
 
 
 def test_patchify_matches_clip_preprocess_unfold():
