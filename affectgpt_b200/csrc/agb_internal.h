@@ -97,9 +97,8 @@ int layernorm512_bf16_gelu(bf16* x, int64_t rows, const float* gamma, const floa
 int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale,
                        cudaStream_t s);
 
-// attention_tc.cu: tcgen05 path; returns -1 when no instantiation covers the shape
-int attention_tc(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s);
-// attention_tc2.cu: two CTAs per SM, eight softmax warps per CTA; same contract
+// attention_tc2.cu: tcgen05 path (S / P / O in TMEM, two CTAs per SM); returns -1 when no instantiation covers the
+// shape (the caller then falls back to the mma.sync kernel)
 int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s);
 
 // vit.cu -------------------------------------------------------------------------------------

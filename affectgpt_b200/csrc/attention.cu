@@ -10,8 +10,6 @@
 //
 // Replaces: CLIPAttention.forward (modeling_clip.py:262-332, scale 1/8, fp32 softmax) and
 // HubertAttention.forward (modeling_hubert.py:262-370).
-#include <cstring>
-
 #include "agb_internal.h"
 #include "agb_ptx.cuh"
 
@@ -196,17 +194,13 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
               "attention: alignment");
   LaunchTimer timer(PROF_ATTENTION, 4.0 * nseq * 16.0 * (double)seq_valid * seq_valid * 64.0,
                     (double)nseq * seq_valid * 4096.0 * 2.0, s);
-  static int mode = -1;   // bring-up switch AGB_ATTENTION: "hmma" = mma.sync kernel, "tc1" = first tcgen05 kernel, default tc2
-  if (mode < 0) {
+  static int force_hmma = -1;   // AGB_ATTENTION=hmma forces the mma.sync kernel (A/B comparisons, tools/attn_bench.py)
+  if (force_hmma < 0) {
     const char* e = getenv("AGB_ATTENTION");
-    mode = (e == nullptr) ? 2 : (e[0] == 'h' ? 0 : (strcmp(e, "tc1") == 0 ? 1 : 2));
+    force_hmma = (e != nullptr && e[0] == 'h') ? 1 : 0;
   }
-  if (mode == 2) {
+  if (!force_hmma) {
     const int r = attention_tc2(qkv, out, nseq, seq_stride, seq_valid, scale, s);
-    if (r >= 0) return r;
-  }
-  if (mode >= 1) {
-    const int r = attention_tc(qkv, out, nseq, seq_stride, seq_valid, scale, s);
     if (r >= 0) return r;
   }
   if (seq_valid <= 112) return launch_mha<7>(qkv, out, nseq, seq_stride, seq_valid, scale, s);

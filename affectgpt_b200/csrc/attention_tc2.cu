@@ -1,10 +1,14 @@
-// tcgen05 multi-head attention, second generation: two co-resident CTAs per SM, eight softmax warps per CTA.
+// tcgen05 multi-head attention: S, P and O live in TMEM, two co-resident CTAs per SM, eight softmax warps per CTA.
 //
 // Shapes on the path: ViT 257 tokens (16 heads x 64) and HuBERT 99 frames; non-causal, K/V of a head fit in smem.
-// The kernel is bound by the exponentials (MUFU: 16/clk/SM -> 257^2/16 = 4128 clk per (frame, head) against 2064 clk of
-// tensor work), so the structure is chosen to keep the MUFU pipe of every SM sub-partition fed:
+// Per (frame, head) the tensor cores need ~2064 clk; the softmax needs 257^2 exponentials plus ~3 more instructions
+// per score.  What the measurements say (profiles/r01_ncu_mha_tc2_summary.txt): the kernel is
+// NOT bound by the SFU - routing half of the exponentials through an FMA-pipe polynomial made it 30 % slower - but by
+// how many softmax warps are runnable per SM sub-partition while the tile's serial chain
+// Q.K^T -> max -> exp -> P.V -> drain is in flight.  Hence:
 //
-//   * TMEM budget 256 columns per CTA -> 2 CTAs per SM; while one CTA's tensor work runs the other one exponentiates.
+//   * TMEM budget 256 columns per CTA -> 2 CTAs per SM: while one CTA's tensor work runs the other one exponentiates,
+//     and every sub-partition has 4 softmax warps to pick from.
 //   * softmax group A (warps 4-7) and group B (warps 8-11) split the key columns of the same 128 query rows
 //     (a warp may only touch TMEM lanes 32*(warp%4)..+31, so A/B warps with the same warp%4 share rows);
 //     row max and row sum are exchanged through shared memory.
@@ -154,14 +158,25 @@ __device__ __forceinline__ float chunk_exp(uint32_t s_addr, uint32_t p_addr, int
   tmem_ld_wait();
   float l1 = 0.f;
   if (key0 + W <= valid) {
+    // packed fp32x2 FMA / ADD (Blackwell FFMA2 / FADD2): 2.75 instead of 3.5 issue slots per exponential
+    uint64_t sc2, mo2, acc;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(sc));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(mo2) : "f"(-mo));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(l), "f"(l1));
 #pragma unroll
     for (int j = 0; j < W; j += 2) {
-      const float p0 = ex2_approx(fmaf(__uint_as_float(v[j]), sc, -mo));
-      const float p1 = ex2_approx(fmaf(__uint_as_float(v[j + 1]), sc, -mo));
-      l += p0;
-      l1 += p1;
+      uint64_t s2, x2, p2;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(s2) : "r"(v[j]), "r"(v[j + 1]));
+      asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(s2), "l"(sc2), "l"(mo2));
+      float x0, x1;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
+      const float p0 = ex2_approx(x0);
+      const float p1 = ex2_approx(x1);
+      asm("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(p0), "f"(p1));
+      asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(p2));
       v[j >> 1] = pack_bf16x2(p0, p1);
     }
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(l1) : "l"(acc));
   } else {
 #pragma unroll
     for (int j = 0; j < W; j += 2) {

@@ -156,6 +156,9 @@ def test_attention_peaked_rows(nseq, stride, valid):
     qkv[:, :1024] *= 6.0
     x = qkv.float().reshape(nseq, stride, 3, 16, 64)
     x[:, valid - 1, 1] = x[:, 0, 0] * 0.5            # last key aligned with query 0 of every head
+    x[:, valid - 30, 1] = x[:, 5, 0] * 0.5           # a late key dominates query 5 (second key block when valid = 257)
+    x[:, 17, 1] = x[:, 9, 0] * 0.5                   # an early key dominates query 9
+    x[:, 3, 1] = x[:, valid - 1, 0] * 0.5            # ... and the last query (the odd 257th row)
     qkv = x.reshape(nseq * stride, 3072).to(torch.bfloat16).contiguous()
     got = ops.attention(qkv, nseq, stride, valid).float().reshape(nseq, stride, 16, 64)[:, :valid]
     x = qkv.float().reshape(nseq, stride, 3, 16, 64)[:, :valid]
