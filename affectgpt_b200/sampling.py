@@ -31,6 +31,21 @@ def uniform_frame_indices(vlen: int, n_frms: int = 8) -> List[int]:
     return idx
 
 
+def headtail_frame_indices(vlen: int, n_frms: int = 8, rng=None) -> List[int]:
+    """sampling == 'headtail' (video_processor.py:213-216): n//2 random frames from each half, drawn with Python's
+    ``random.sample`` in this order (first half, then second half) so that a caller who seeds ``random`` the way the
+    reference process does gets the reference's indices."""
+    import random as _random
+    rng = rng or _random
+    n = min(n_frms, vlen)
+    head = sorted(rng.sample(range(vlen // 2), n // 2))
+    tail = sorted(rng.sample(range(vlen // 2, vlen), n // 2))
+    idx = head + tail
+    while len(idx) < n_frms:
+        idx.append(idx[-1])
+    return idx
+
+
 def emotion_peak_frame_indices(vlen: int, au_info: Optional[dict] = None, n_frms: int = 8) -> List[int]:
     """sampling == 'emotion_peak' (video_processor.py:217-244): without au_info the middle frame repeated."""
     idx = smart_frame_indices(au_info, vlen) if au_info else [vlen // 2]

@@ -28,6 +28,19 @@ def uniform_indices(vlen: int, n_frms: int = 8) -> List[int]:
     return indices
 
 
+def headtail_indices(vlen: int, n_frms: int = 8, rng=None) -> List[int]:
+    """video_processor.py:213-216 + pad :243-244; ``rng`` defaults to the ``random`` module like the reference."""
+    import random as rnd
+    rng = rng or rnd
+    n = min(n_frms, vlen)
+    indices_h = sorted(rng.sample(range(vlen // 2), n // 2))
+    indices_t = sorted(rng.sample(range(vlen // 2, vlen), n // 2))
+    indices = indices_h + indices_t
+    while len(indices) < n_frms:
+        indices.append(indices[-1])
+    return indices
+
+
 def smart_frame_indices(au_info: Optional[dict], total_video_frames: int) -> List[int]:
     if not au_info or "peak_frames" not in au_info or len(au_info["peak_frames"]) == 0:
         return sorted(np.linspace(0, total_video_frames - 1, 8).astype(int).tolist())

@@ -1,0 +1,114 @@
+"""Parity pinned against the REFERENCE's own code: fixtures in tests/golden/reference_*.{json,npz} were produced by
+executing /root/reference/AffectGPT's unmodified sources in the build container (tests/golden/make_reference_golden.py
++ ref_loader.py).  Here the oracle (oracle/) and the product's host code (affectgpt_b200/) are held to them:
+integer contracts bit-exact, fp32 fusion math to 1e-5.  CPU only."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from affectgpt_b200 import sampling as S
+from oracle import qformer as OQ
+from oracle import reference_path as R
+from oracle import sampling as OS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_sampling.json")) as f:
+    SAMP = json.load(f)
+FUS = np.load(os.path.join(HERE, "golden", "reference_fusion.npz"))
+
+
+@pytest.mark.parametrize("impl", ["host", "oracle"])
+def test_uniform_indices_match_reference(impl):
+    fn = S.uniform_frame_indices if impl == "host" else OS.uniform_indices
+    for n, table in ((8, SAMP["uniform8"]), (16, SAMP["uniform16"])):
+        for vlen, want in table.items():
+            assert fn(int(vlen), n) == want, (vlen, n)
+    for vlen, want in SAMP["face_uniform8"].items():            # load_face uses the same rule (:272-283)
+        assert fn(int(vlen), 8) == want
+
+
+@pytest.mark.parametrize("impl", ["host", "oracle"])
+def test_emotion_peak_indices_match_reference(impl):
+    peak = S.emotion_peak_frame_indices if impl == "host" else OS.emotion_peak_indices
+    smart = S.smart_frame_indices if impl == "host" else OS.smart_frame_indices
+    for vlen, want in SAMP["emotion_peak_noinfo"].items():
+        assert peak(int(vlen), None, 8) == want
+    for case in SAMP["smart"]:
+        assert smart(case["au_info"], case["total_video_frames"]) == case["indices"], case
+    for case in SAMP["emotion_peak_json"]:
+        assert peak(case["vlen"], case["au_info"], 8) == case["indices"], case
+
+
+@pytest.mark.parametrize("impl", ["host", "oracle"])
+def test_headtail_indices_match_reference_rng_stream(impl):
+    fn = S.headtail_frame_indices if impl == "host" else OS.headtail_indices
+    for case in SAMP["headtail"]:
+        random.seed(case["seed"])
+        assert fn(case["vlen"], 8) == case["indices"], case
+
+
+@pytest.mark.parametrize("impl", ["host", "oracle"])
+def test_audio_segments_match_reference(impl):
+    for case in SAMP["audio"]:
+        n, ch = case["n"], case["channels"]
+        base = torch.arange(n, dtype=torch.float32) + 1.0        # sample k holds k + 1, zero = padding
+        wav = torch.stack([base, base]) if ch == 2 else base[None]
+        clips = S.segment_audio(wav) if impl == "host" else OS.audio_segments(wav)[0]
+        assert tuple(clips.shape) == (8, 1, 32000)
+        assert [int(x) - 1 for x in clips[:, 0, 0]] == case["starts"], case
+        assert [int(x) - 1 for x in clips[:, 0, -1]] == case["last_sample"], case
+        if impl == "host":
+            bounds = S.audio_segment_bounds(n)
+            assert [a for a, _ in bounds] == [max(s, 0) for s in case["starts"]]
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(7)
+    frame_h = torch.randn(3, 8, 768, generator=g)
+    face_h = torch.randn(3, 8, 768, generator=g)
+    audio_h = torch.randn(3, 8, 1024, generator=g)
+    frame_vec = torch.randn(3, 768, generator=g)
+    return frame_h, face_h, audio_h, frame_vec
+
+
+def _close(got, key, tol=1e-5):
+    want = torch.from_numpy(FUS[key])
+    assert tuple(got.shape) == tuple(want.shape), (key, got.shape, want.shape)
+    err = float((got - want).abs().max()) / max(float(want.abs().max()), 1e-12)
+    assert err < tol, (key, err)
+
+
+def test_oracle_attention_and_mean_heads_match_reference():
+    st = R.build_fusion_state(seed=1234)
+    frame_h, face_h, audio_h, frame_vec = _inputs()
+    _close(R.encode_video_attention_realtime(st, frame_h)[1], "att_video_realtime_llm")
+    _close(R.encode_video_attention_realtime(st, frame_h)[1], "att_video_merge_realtime_llm")
+    _close(R.encode_video_attention(st, face_h)[1], "att_video_pre3d_llm")
+    _close(R.encode_video_attention(st, frame_vec)[1], "att_video_pre2d_llm")
+    _close(R.encode_video_attention(st, frame_vec)[0], "att_video_pre2d_hidden")
+    _close(R.encode_audio_attention(st, audio_h)[1], "att_audio_realtime_llm")
+    _close(R.encode_audio_attention(st, audio_h)[1], "att_audio_pre_llm")
+    mh, ml = R.encode_multi_attention(st, face_h, audio_h)
+    _close(mh, "att_multi_hidden")
+    _close(ml, "att_multi_llm")
+    _close(R.encode_video_attention(st, frame_h, fusion_type="mean")[1], "mean_video_realtime_llm")
+    _close(R.encode_video_attention(st, face_h, fusion_type="mean")[1], "mean_video_pre3d_llm")
+    _close(R.encode_audio_attention(st, audio_h, fusion_type="mean")[1], "mean_audio_realtime_llm")
+    _close(R.encode_audio_attention(st, audio_h, fusion_type="mean")[1], "mean_audio_pre_llm")
+
+
+def test_oracle_qformer_variants_match_reference():
+    qs = OQ.fusion_qformer_state(seed=4321, n_query=4)
+    frame_h, face_h, audio_h, frame_vec = _inputs()
+    with torch.no_grad():
+        _close(OQ.encode_video_qformer(qs, frame_h)[1], "qf_video_realtime_llm")
+        _close(OQ.encode_video_qformer(qs, face_h)[1], "qf_video_pre3d_llm")
+        _close(OQ.encode_video_qformer(qs, frame_vec.unsqueeze(1))[1], "qf_video_pre2d_llm")
+        _close(OQ.encode_audio_qformer(qs, audio_h)[1], "qf_audio_realtime_llm")
+        mh, ml = OQ.encode_multi_qformer(qs, face_h, audio_h)
+        _close(mh, "qf_multi_hidden")
+        _close(ml, "qf_multi_llm")
