@@ -20,7 +20,8 @@ class AgbCfg(C.Structure):
     _fields_ = [
         ("vit_layers", C.c_int32), ("hubert_layers", C.c_int32), ("hubert_conv_norm", C.c_int32),
         ("hubert_do_normalize", C.c_int32), ("llm_dim", C.c_int32), ("max_frames_per_chunk", C.c_int32),
-        ("max_segments_per_chunk", C.c_int32), ("reserved", C.c_int32 * 9),
+        ("max_segments_per_chunk", C.c_int32), ("qf_video_queries", C.c_int32), ("qf_audio_queries", C.c_int32),
+        ("qf_multi_queries", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "agb_video_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "agb_audio_fuse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "agb_multi_fuse": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "agb_qformer_fuse": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "agb_set_tap": (_i, [_vp, C.c_char_p, _vp, _i64]),
     "agb_launch_count": (_i64, []),
     "agb_profile_begin": (_i, []),

@@ -82,6 +82,10 @@ struct agb_ctx {
   int64_t h_stat_cap = 0;
   int64_t f_cap = 0;
   float *f_a = nullptr, *f_b = nullptr, *f_c = nullptr, *f_d = nullptr, *f_e = nullptr;
+  // ---- Q-Former variants (fp32): [0] video, [1] audio, [2] multi; multi also owns its 768/1024 -> 1024 embeddings
+  QFormerW qf[3];
+  float *qf_mv_w = nullptr, *qf_mv_b = nullptr, *qf_ma_w = nullptr, *qf_ma_b = nullptr;
+  QFormerWs qf_ws;
 };
 
 namespace {
@@ -270,6 +274,59 @@ int register_weights(agb_ctx* c) {
     if (int r = reg_f32(c, std::string("fusion.") + e.name + ".weight", {e.out, e.in}, &c->f[std::string(e.name) + ".weight"])) return r;
     if (int r = reg_f32(c, std::string("fusion.") + e.name + ".bias", {e.out}, &c->f[std::string(e.name) + ".bias"])) return r;
   }
+  // ------------------------------------------------------------------ Q-Former variants (built only when requested)
+  struct QS { const char* fam; const char* stem; const char* pos_key; int pos_rows; int enc_width; int nq; const char* proj; };
+  const QS qs[3] = {
+      {"qf_video.", "video", "video_frame_position_embedding.weight", 32, 768, c->cfg.qf_video_queries, "affectgpt_proj"},
+      {"qf_audio.", "audio", "audio_position_embedding.weight", 8, 1024, c->cfg.qf_audio_queries, "audio_llama_proj"},
+      {"qf_multi.", "multi", "multi_position_embedding.weight", 264, 1024, c->cfg.qf_multi_queries, "multi_llama_proj"}};
+  for (int i = 0; i < 3; ++i) {
+    const QS& q = qs[i];
+    if (q.nq <= 0) continue;
+    QFormerW& W = c->qf[i];
+    W.nq = q.nq; W.enc_width = q.enc_width; W.pos_rows = q.pos_rows;
+    const std::string F = q.fam, S = q.stem;
+    if (int r = reg_f32(c, F + q.pos_key, {q.pos_rows, q.enc_width}, &W.pos)) return r;
+    if (int r = reg_f32(c, F + S + "_query_tokens", {1, q.nq, 768}, &W.query)) return r;
+    if (int r = reg_f32(c, F + q.proj + ".weight", {D, 768}, &W.proj_w)) return r;
+    if (int r = reg_f32(c, F + q.proj + ".bias", {D}, &W.proj_b)) return r;
+    const std::string Bk = F + S + "_Qformer.bert.";
+    if (int r = reg_f32(c, Bk + "embeddings.LayerNorm.weight", {768}, &W.emb_g)) return r;
+    if (int r = reg_f32(c, Bk + "embeddings.LayerNorm.bias", {768}, &W.emb_b)) return r;
+    for (int l = 0; l < 2; ++l) {
+      QFLayerW& L = W.layer[l];
+      const std::string P = Bk + "encoder.layer." + std::to_string(l) + ".";
+      struct LW { const char* key; int out, in; float** w; float** b; };
+      const LW lw[] = {{"attention.self.query", 768, 768, &L.sq_w, &L.sq_b},
+                       {"attention.self.key", 768, 768, &L.sk_w, &L.sk_b},
+                       {"attention.self.value", 768, 768, &L.sv_w, &L.sv_b},
+                       {"attention.output.dense", 768, 768, &L.so_w, &L.so_b},
+                       {"crossattention.self.query", 768, 768, &L.cq_w, &L.cq_b},
+                       {"crossattention.self.key", 768, q.enc_width, &L.ck_w, &L.ck_b},
+                       {"crossattention.self.value", 768, q.enc_width, &L.cv_w, &L.cv_b},
+                       {"crossattention.output.dense", 768, 768, &L.co_w, &L.co_b},
+                       {"intermediate_query.dense", 3072, 768, &L.fi_w, &L.fi_b},
+                       {"output_query.dense", 768, 3072, &L.fo_w, &L.fo_b}};
+      for (const LW& e : lw) {
+        if (int r = reg_f32(c, P + e.key + ".weight", {e.out, e.in}, e.w)) return r;
+        if (int r = reg_f32(c, P + e.key + ".bias", {e.out}, e.b)) return r;
+      }
+      struct LN { const char* key; float** g; float** b; };
+      const LN ln[] = {{"attention.output.LayerNorm", &L.sln_g, &L.sln_b},
+                       {"crossattention.output.LayerNorm", &L.cln_g, &L.cln_b},
+                       {"output_query.LayerNorm", &L.fln_g, &L.fln_b}};
+      for (const LN& e : ln) {
+        if (int r = reg_f32(c, P + e.key + ".weight", {768}, e.g)) return r;
+        if (int r = reg_f32(c, P + e.key + ".bias", {768}, e.b)) return r;
+      }
+    }
+    if (i == 2) {
+      if (int r = reg_f32(c, F + "multi_video_embs.weight", {1024, 768}, &c->qf_mv_w)) return r;
+      if (int r = reg_f32(c, F + "multi_video_embs.bias", {1024}, &c->qf_mv_b)) return r;
+      if (int r = reg_f32(c, F + "multi_audio_embs.weight", {1024, 1024}, &c->qf_ma_w)) return r;
+      if (int r = reg_f32(c, F + "multi_audio_embs.bias", {1024}, &c->qf_ma_b)) return r;
+    }
+  }
   return 0;
 }
 
@@ -278,6 +335,19 @@ int check_family_loaded(agb_ctx* c, const std::string& family) {
     if (kv.first.compare(0, family.size() + 1, family + ".") == 0 && !kv.second.loaded) {
       set_error("weights not loaded: " + kv.first + " (and possibly more; see agb_missing_count)");
       return 4;
+    }
+  return 0;
+}
+
+// the attention / mean heads are loaded per variant in use: check exactly the tensors a call reads
+int check_heads_loaded(agb_ctx* c, std::initializer_list<const char*> heads) {
+  for (const char* h : heads)
+    for (const char* suffix : {".weight", ".bias"}) {
+      auto it = c->loaders.find(std::string("fusion.") + h + suffix);
+      if (it == c->loaders.end() || !it->second.loaded) {
+        set_error(std::string("weights not loaded: fusion.") + h + suffix);
+        return 4;
+      }
     }
   return 0;
 }
@@ -614,7 +684,8 @@ int agb_video_fuse(agb_ctx* ctx, const float* H, int B, int T, int fusion_type, 
   if (!ctx) { set_error("agb_video_fuse: null context"); return 2; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (B == 0) return 0;
-  if (int r = check_family_loaded(ctx, "fusion")) return fail(ctx, r);
+  if (int r = fusion_type == AGB_FUSE_ATTENTION ? check_heads_loaded(ctx, {"video_attention_mlp", "affectgpt_proj"})
+                                                : check_heads_loaded(ctx, {"affectgpt_proj"})) return fail(ctx, r);
   if (int r = ensure_fuse_ws(ctx, B)) return fail(ctx, r);
   int r;
   if (fusion_type == AGB_FUSE_ATTENTION)
@@ -632,7 +703,8 @@ int agb_audio_fuse(agb_ctx* ctx, const float* H, int B, int T, int fusion_type, 
   if (!ctx) { set_error("agb_audio_fuse: null context"); return 2; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (B == 0) return 0;
-  if (int r = check_family_loaded(ctx, "fusion")) return fail(ctx, r);
+  if (int r = fusion_type == AGB_FUSE_ATTENTION ? check_heads_loaded(ctx, {"audio_attention_mlp", "audio_llama_proj"})
+                                                : check_heads_loaded(ctx, {"audio_llama_proj"})) return fail(ctx, r);
   if (int r = ensure_fuse_ws(ctx, B)) return fail(ctx, r);
   int r;
   if (fusion_type == AGB_FUSE_ATTENTION)
@@ -651,7 +723,8 @@ int agb_multi_fuse(agb_ctx* ctx, const float* Hv, int Tv, const float* Ha, int T
   if (!ctx) { set_error("agb_multi_fuse: null context"); return 2; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (B == 0) return 0;
-  if (int r = check_family_loaded(ctx, "fusion")) return fail(ctx, r);
+  if (int r = check_heads_loaded(ctx, {"multi_video_embs", "multi_audio_embs", "attention_mlp", "fc_att", "multi_llama_proj"}))
+    return fail(ctx, r);
   if (int r = ensure_fuse_ws(ctx, B)) return fail(ctx, r);
   auto& f = ctx->f;
   int r;
@@ -672,6 +745,80 @@ int agb_multi_fuse(agb_ctx* ctx, const float* Hv, int Tv, const float* Ha, int T
   if ((r = weighted_pair_sum(ctx->f_a, ctx->f_b, ctx->f_e, B, 1024, multi_hidden, s))) return fail(ctx, r);
   r = linear_f32(multi_hidden, 1024, f["multi_llama_proj.weight"], f["multi_llama_proj.bias"], llm, ctx->cfg.llm_dim, B,
                  ctx->cfg.llm_dim, 1024, s);
+  return r ? fail(ctx, r) : 0;
+}
+
+namespace {
+int ensure_qf_ws(agb_ctx* c, int64_t q_rows, int64_t kv_rows, int64_t enc_elems) {
+  QFormerWs& w = c->qf_ws;
+  if (q_rows > w.cap_q) {
+    void* old[] = {w.x, w.t0, w.t1, w.t2, w.ff};
+    for (void* p : old) dev_free(c, p);
+    if (int r = dev_alloc(c, &w.x, (size_t)q_rows * 768)) return r;
+    if (int r = dev_alloc(c, &w.t0, (size_t)q_rows * 768)) return r;
+    if (int r = dev_alloc(c, &w.t1, (size_t)q_rows * 768)) return r;
+    if (int r = dev_alloc(c, &w.t2, (size_t)q_rows * 768)) return r;
+    if (int r = dev_alloc(c, &w.ff, (size_t)q_rows * 3072)) return r;
+    w.cap_q = q_rows;
+  }
+  if (kv_rows > w.cap_kv) {
+    dev_free(c, w.kx); dev_free(c, w.vx);
+    if (int r = dev_alloc(c, &w.kx, (size_t)kv_rows * 768)) return r;
+    if (int r = dev_alloc(c, &w.vx, (size_t)kv_rows * 768)) return r;
+    w.cap_kv = kv_rows;
+  }
+  if (enc_elems > w.cap_enc) {
+    dev_free(c, w.enc); dev_free(c, w.ev); dev_free(c, w.ea);
+    if (int r = dev_alloc(c, &w.enc, (size_t)enc_elems)) return r;
+    if (int r = dev_alloc(c, &w.ev, (size_t)enc_elems)) return r;
+    if (int r = dev_alloc(c, &w.ea, (size_t)enc_elems)) return r;
+    w.cap_enc = enc_elems;
+  }
+  return 0;
+}
+}  // namespace
+
+int agb_qformer_fuse(agb_ctx* ctx, int which, const float* Hv, int Tv, const float* Ha, int Ta, int B, float* hidden,
+                     float* llm, void* stream) {
+  if (!ctx) { set_error("agb_qformer_fuse: null context"); return 2; }
+  if (which < 0 || which > 2) { set_error("agb_qformer_fuse: which must be 0 (video), 1 (audio) or 2 (multi)"); return fail(ctx, 2); }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B == 0) return 0;
+  const QFormerW& W = ctx->qf[which];
+  static const char* fam[3] = {"qf_video", "qf_audio", "qf_multi"};
+  if (W.nq <= 0) {
+    set_error(std::string("agb_qformer_fuse: the ") + fam[which] + " Q-Former was not configured (agb_cfg.qf_*_queries == 0)");
+    return fail(ctx, 2);
+  }
+  if (int r = check_family_loaded(ctx, fam[which])) return fail(ctx, r);
+  const bool need_v = which != AGB_QF_AUDIO, need_a = which != AGB_QF_VIDEO;
+  if ((need_v && (!Hv || Tv <= 0)) || (need_a && (!Ha || Ta <= 0)) || !llm) {
+    set_error("agb_qformer_fuse: missing input / output for this variant");
+    return fail(ctx, 2);
+  }
+  const int T = (need_v ? Tv : 0) + (need_a ? Ta : 0);
+  if (T > W.pos_rows) {
+    set_error("agb_qformer_fuse: " + std::to_string(T) + " encoder tokens exceed the position embedding table (" +
+              std::to_string(W.pos_rows) + " rows)");
+    return fail(ctx, 2);
+  }
+  const int64_t q_rows = (int64_t)B * W.nq, kv_rows = (int64_t)B * (T > W.nq ? T : W.nq);
+  if (int r = ensure_qf_ws(ctx, q_rows, kv_rows, (int64_t)B * T * 1024)) return fail(ctx, r);
+  QFormerWs& ws = ctx->qf_ws;
+  int r;
+  if (which == AGB_QF_VIDEO) {                       // frames + video_frame_position_embedding (:439-451)
+    if ((r = add_position_f32(Hv, W.pos, B, Tv, 768, 0, Tv, ws.enc, s))) return fail(ctx, r);
+  } else if (which == AGB_QF_AUDIO) {                // segments + audio_position_embedding (:645-648)
+    if ((r = add_position_f32(Ha, W.pos, B, Ta, 1024, 0, Ta, ws.enc, s))) return fail(ctx, r);
+  } else {                                           // both streams to 1024, concatenated along t, + position (:855-865)
+    if ((r = linear_f32(Hv, 768, ctx->qf_mv_w, ctx->qf_mv_b, ws.ev, 1024, B * Tv, 1024, 768, s))) return fail(ctx, r);
+    if ((r = linear_f32(Ha, 1024, ctx->qf_ma_w, ctx->qf_ma_b, ws.ea, 1024, B * Ta, 1024, 1024, s))) return fail(ctx, r);
+    if ((r = add_position_f32(ws.ev, W.pos, B, Tv, 1024, 0, T, ws.enc, s))) return fail(ctx, r);
+    if ((r = add_position_f32(ws.ea, W.pos, B, Ta, 1024, Tv, T, ws.enc, s))) return fail(ctx, r);
+  }
+  if ((r = qformer_forward_f32(W, ws.enc, B, T, ws, s))) return fail(ctx, r);
+  if (hidden) AGB_CHECK_CUDA(cudaMemcpyAsync(hidden, ws.x, (size_t)q_rows * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  r = linear_f32(ws.x, 768, W.proj_w, W.proj_b, llm, ctx->cfg.llm_dim, (int)q_rows, ctx->cfg.llm_dim, 768, s);
   return r ? fail(ctx, r) : 0;
 }
 

@@ -131,6 +131,33 @@ int mean_over_t(const float* H, int B, int T, int D, float* out, cudaStream_t s)
 int weighted_pair_sum(const float* v, const float* a, const float* att, int B, int D, float* out, cudaStream_t s);
 int concat2_f32(const float* a, const float* b, int B, int Da, int Db, float* out, cudaStream_t s);
 
+// qformer.cu ---------------------------------------------------------------------------------
+struct QFLayerW {   // reference keys under <x>_Qformer.bert.encoder.layer.<i>.
+  float *sq_w, *sq_b, *sk_w, *sk_b, *sv_w, *sv_b, *so_w, *so_b, *sln_g, *sln_b;   // attention.{self.*,output.*}
+  float *cq_w, *cq_b, *ck_w, *ck_b, *cv_w, *cv_b, *co_w, *co_b, *cln_g, *cln_b;   // crossattention.{...}
+  float *fi_w, *fi_b, *fo_w, *fo_b, *fln_g, *fln_b;                               // intermediate_query / output_query
+};
+struct QFormerW {
+  int nq = 0, enc_width = 0, pos_rows = 0;
+  float *emb_g = nullptr, *emb_b = nullptr;     // bert.embeddings.LayerNorm
+  float *query = nullptr;                       // <x>_query_tokens [1, nq, 768]
+  float *pos = nullptr;                         // position embedding [pos_rows, enc_width]
+  float *proj_w = nullptr, *proj_b = nullptr;   // projector 768 -> llm_dim
+  QFLayerW layer[2] = {};
+};
+struct QFormerWs {
+  float *x = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *kx = nullptr, *vx = nullptr, *ff = nullptr,
+        *enc = nullptr, *ev = nullptr, *ea = nullptr;
+  int64_t cap_q = 0, cap_kv = 0, cap_enc = 0;
+};
+int ln_residual_f32(const float* x, int x_rows, const float* res, int64_t rows, int D, const float* g, const float* b,
+                    float eps, float* y, cudaStream_t s);
+int add_position_f32(const float* in, const float* pos, int B, int T, int D, int t0, int T_total, float* out,
+                     cudaStream_t s);
+int gelu_erf_f32_inplace(float* x, int64_t n, cudaStream_t s);
+int mha12x64_f32(const float* q, const float* k, const float* v, int B, int Tq, int Tk, float* out, cudaStream_t s);
+int qformer_forward_f32(const QFormerW& W, const float* enc, int B, int T, QFormerWs& ws, cudaStream_t s);
+
 // pack.cu ------------------------------------------------------------------------------------
 int convert_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
 // dst[r, c] (row stride ld_dst) = src[r, c] for r<rows, c<cols; zero-fills c in [cols, cols_pad)

@@ -30,7 +30,8 @@ class Engine:
 
     def __init__(self, device="cuda:0", vit_layers: int = 24, hubert_layers: int = 24,
                  feat_extract_norm: str = "layer", do_normalize: bool = True, llm_dim: int = 3584,
-                 max_frames_per_chunk: int = 512, max_segments_per_chunk: int = 512):
+                 max_frames_per_chunk: int = 512, max_segments_per_chunk: int = 512, qf_video_queries: int = 0,
+                 qf_audio_queries: int = 0, qf_multi_queries: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("affectgpt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if feat_extract_norm not in ("layer", "group"):
@@ -50,6 +51,8 @@ class Engine:
         cfg.llm_dim = llm_dim
         cfg.max_frames_per_chunk = max_frames_per_chunk
         cfg.max_segments_per_chunk = max_segments_per_chunk
+        cfg.qf_video_queries, cfg.qf_audio_queries, cfg.qf_multi_queries = qf_video_queries, qf_audio_queries, qf_multi_queries
+        self.qf_queries = {"video": qf_video_queries, "audio": qf_audio_queries, "multi": qf_multi_queries}
         self.cfg = cfg
         self.llm_dim = llm_dim
         self._ctx = C.c_void_p()
@@ -75,10 +78,10 @@ class Engine:
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, family: str, state_dict: Dict[str, torch.Tensor], strict: bool = True) -> Tuple[list, list]:
-        """Load checkpoint tensors of one family ("clip", "hubert", "fusion") by their checkpoint keys
-        (SURVEY appendix B).  Returns (missing, unexpected) like nn.Module.load_state_dict; with
-        ``strict`` a missing tensor raises RuntimeError."""
-        assert family in ("clip", "hubert", "fusion")
+        """Load checkpoint tensors of one family ("clip", "hubert", "fusion", "qf_video", "qf_audio", "qf_multi") by
+        their checkpoint keys (SURVEY appendix B).  Returns (missing, unexpected) like nn.Module.load_state_dict;
+        with ``strict`` a missing tensor raises RuntimeError."""
+        assert family in ("clip", "hubert", "fusion", "qf_video", "qf_audio", "qf_multi")
         unexpected = []
         stream = _stream_ptr(self.device)
         with torch.cuda.device(self.device):
@@ -170,6 +173,32 @@ class Engine:
             self._check(self.lib.agb_multi_fuse(self._ctx, _ptr(hv), tv, _ptr(ha), ta, b, _ptr(multi), _ptr(llm),
                                                 _stream_ptr(self.device)), "agb_multi_fuse")
         return multi, llm
+
+    def qformer_fuse(self, which: str, video_hidden: Optional[torch.Tensor] = None,
+                     audio_hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``*_fusion_type == 'qformer'``: -> (query hidden [b,n_q,768], llm [b,n_q,llm_dim]).  which: 'video'
+        (video_hidden [b,t,768]), 'audio' (audio_hidden [b,t,1024]) or 'multi' (both)."""
+        code = {"video": 0, "audio": 1, "multi": 2}[which]
+        nq = self.qf_queries[which]
+        if nq <= 0:
+            raise RuntimeError(f"engine was created without a {which} Q-Former (qf_{which}_queries == 0)")
+        hv = video_hidden.to(device=self.device, dtype=torch.float32).contiguous() if video_hidden is not None else None
+        ha = audio_hidden.to(device=self.device, dtype=torch.float32).contiguous() if audio_hidden is not None else None
+        ref = hv if hv is not None else ha
+        if ref is None:
+            raise ValueError("qformer_fuse needs at least one input")
+        b = ref.shape[0]
+        if hv is not None:
+            assert hv.dim() == 3 and hv.shape[2] == 768 and hv.shape[0] == b
+        if ha is not None:
+            assert ha.dim() == 3 and ha.shape[2] == 1024 and ha.shape[0] == b
+        hidden = torch.empty((b, nq, 768), dtype=torch.float32, device=self.device)
+        llm = torch.empty((b, nq, self.llm_dim), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.agb_qformer_fuse(self._ctx, code, _ptr(hv), hv.shape[1] if hv is not None else 0,
+                                                  _ptr(ha), ha.shape[1] if ha is not None else 0, b, _ptr(hidden),
+                                                  _ptr(llm), _stream_ptr(self.device)), "agb_qformer_fuse")
+        return hidden, llm
 
     # ------------------------------------------------------------------ debug taps
     def tap(self, name: str, shape: Iterable[int], dtype=torch.float32) -> torch.Tensor:

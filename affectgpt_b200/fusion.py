@@ -6,9 +6,10 @@ reference's ``ckpt['model']`` keys (``video_attention_mlp.*``, ``affectgpt_proj.
 ``audio_llama_proj.*``, ``multi_video_embs.*``, ``multi_audio_embs.*``, ``attention_mlp.*``, ``fc_att.*``,
 ``multi_llama_proj.*``; affectgpt.py:1099-1120) and are loaded non-strictly, as the reference does.
 
-Scope: the shipping ``attention`` fusion (every config in train_configs/) and ``mean``.  The Q-Former
-variants are not built yet and raise NotImplementedError (DESIGN.md "next").  The LLM, LoRA and the loss are
-out of scope: this class stops at the fused tokens.
+Scope: all three ``*_fusion_type`` values of the reference - the shipping ``attention`` fusion (every config in
+train_configs/), ``mean`` and ``qformer`` (encode_video_qformer :420-468, encode_audio_qformer :628-664,
+encode_multi_qformer :848-881; weights ``*_Qformer.*``, ``*_query_tokens``, ``*position_embedding.weight``).  The LLM,
+LoRA and the loss are out of scope: this class stops at the fused tokens.
 """
 from __future__ import annotations
 
@@ -22,6 +23,15 @@ from .encoders import CLIP_VIT_LARGE, HUBERT_LARGE
 from .engine import Engine, get_engine
 from .registry import registry
 
+# checkpoint key stems of the Q-Former variants, per engine family (affectgpt.py:157-166, 223-231, 312-327)
+QFORMER_FAMILIES = {
+    "video": ("video_frame_position_embedding", "video_query_tokens", "video_Qformer", "affectgpt_proj"),
+    "audio": ("audio_position_embedding", "audio_query_tokens", "audio_Qformer", "audio_llama_proj"),
+    "multi": ("multi_video_embs", "multi_audio_embs", "multi_position_embedding", "multi_query_tokens", "multi_Qformer",
+              "multi_llama_proj"),
+}
+QFORMER_STEMS = tuple(s for v in QFORMER_FAMILIES.values() for s in v)
+
 FUSION_KEYS = ("video_attention_mlp", "affectgpt_proj", "audio_attention_mlp", "audio_llama_proj", "multi_video_embs",
                "multi_audio_embs", "attention_mlp", "fc_att", "multi_llama_proj")
 
@@ -34,13 +44,11 @@ class AffectGPTFusion(nn.Module):
                  num_multi_query_token: int = 1, llm_dim: int = config.LLM_DIM, engine: Optional[Engine] = None,
                  engine_cfg: Optional[dict] = None):
         super().__init__()
-        for name, ft in (("video", video_fusion_type), ("audio", audio_fusion_type), ("multi", multi_fusion_type)):
-            if ft == "qformer":
-                raise NotImplementedError(f"{name}_fusion_type='qformer' is not built yet (no shipped config uses it)")
-            if ft not in ("attention", "mean"):
+        for name, ft in (("video", video_fusion_type), ("audio", audio_fusion_type)):
+            if ft not in ("attention", "mean", "qformer"):
                 raise ValueError(f"unknown {name}_fusion_type {ft!r}")
-        if multi_fusion_type != "attention":
-            raise ValueError("multi_fusion_type must be 'attention' (affectgpt.py:910-915)")
+        if multi_fusion_type not in ("attention", "qformer"):
+            raise ValueError("multi_fusion_type must be 'attention' or 'qformer' (affectgpt.py:910-915)")
         self.visual_encoder = visual_encoder
         self.acoustic_encoder = acoustic_encoder
         self.video_fusion_type = video_fusion_type
@@ -53,6 +61,13 @@ class AffectGPTFusion(nn.Module):
         self._engine = engine
         self._engine_cfg = dict(engine_cfg or {})
         self._engine_cfg.setdefault("llm_dim", llm_dim)
+        for which, ft, nq in (("video", video_fusion_type, num_video_query_token),
+                              ("audio", audio_fusion_type, num_audio_query_token),
+                              ("multi", multi_fusion_type, num_multi_query_token)):
+            if ft == "qformer":
+                self._engine_cfg.setdefault(f"qf_{which}_queries", nq)
+                if engine is not None and engine.qf_queries[which] != nq:
+                    raise ValueError(f"engine was created with qf_{which}_queries={engine.qf_queries[which]}, need {nq}")
         self._fusion_state: Optional[Dict[str, torch.Tensor]] = None
         if engine is not None:
             for enc in (visual_encoder, acoustic_encoder):
@@ -62,17 +77,39 @@ class AffectGPTFusion(nn.Module):
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, state_dict, strict: bool = False):   # noqa: D401 - nn.Module signature
         """Accepts ``ckpt['model']`` (affectgpt.py:1099-1120); only the fusion/projector keys are consumed."""
-        picked = {k: v for k, v in state_dict.items() if k.split(".")[0] in FUSION_KEYS}
+        picked = {k: v for k, v in state_dict.items() if k.split(".")[0] in FUSION_KEYS or k.split(".")[0] in QFORMER_STEMS}
         self._fusion_state = picked
         if self._engine is not None:
             self._upload()
-        missing = [f"{k}.{s}" for k in FUSION_KEYS for s in ("weight", "bias") if f"{k}.{s}" not in picked]
+        missing = [f"{k}.{s}" for k in self._needed_heads() for s in ("weight", "bias") if f"{k}.{s}" not in picked]
         if strict and missing:
             raise RuntimeError(f"missing keys: {missing}")
         return missing, [k for k in state_dict if k not in picked]
 
+    def _uses_qformer(self, which: str) -> bool:
+        return getattr(self, f"{which}_fusion_type") == "qformer"
+
+    def _needed_heads(self):
+        """Linear heads the configured (non-qformer) variants read; the qformer families are checked by the engine."""
+        need = []
+        if not self._uses_qformer("video"):
+            need += (["video_attention_mlp"] if self.video_fusion_type == "attention" else []) + ["affectgpt_proj"]
+        if not self._uses_qformer("audio"):
+            need += (["audio_attention_mlp"] if self.audio_fusion_type == "attention" else []) + ["audio_llama_proj"]
+        if not self._uses_qformer("multi"):
+            need += ["multi_video_embs", "multi_audio_embs", "attention_mlp", "fc_att", "multi_llama_proj"]
+        return need
+
     def _upload(self):
-        self._engine.load_state_dict("fusion", self._fusion_state, strict=False)
+        st = self._fusion_state
+        # attention / mean heads: only tensors whose shapes are those of the non-qformer variants (the 768-wide
+        # audio / multi projectors of the qformer variants go to their own families below)
+        plain = {k: v for k, v in st.items() if k.split(".")[0] in FUSION_KEYS and k.split(".")[0] in self._needed_heads()}
+        self._engine.load_state_dict("fusion", plain, strict=False)
+        for which, stems in QFORMER_FAMILIES.items():
+            if self._uses_qformer(which):
+                sub = {k: v for k, v in st.items() if k.split(".")[0] in stems}
+                self._engine.load_state_dict(f"qf_{which}", sub, strict=True)
         self._fusion_state = None
 
     def _eng(self, device: torch.device) -> Engine:
@@ -82,7 +119,8 @@ class AffectGPTFusion(nn.Module):
             self._engine = get_engine(device, **self._engine_cfg)
         if self._fusion_state is not None:
             self._upload()
-        miss = self._engine.missing("fusion")
+        need = set(self._needed_heads())
+        miss = [m for m in self._engine.missing("fusion") if m.split(".")[0] in need]
         if miss:
             raise RuntimeError(f"fusion weights not loaded: {miss[:4]} ...")
         return self._engine
@@ -104,6 +142,8 @@ class AffectGPTFusion(nn.Module):
             hidden = self.visual_encoder(video, raw_video)
             bypass = False
         eng = self._eng(hidden.device)
+        if self.video_fusion_type == "qformer":                                # :420-468 / :563-580
+            return hidden, eng.qformer_fuse("video", video_hidden=hidden)[1]
         llm = eng.video_fuse(hidden, self.video_fusion_type, bypass_t1=bypass)
         llm = llm.unsqueeze(1).expand(-1, self.num_video_query_token, -1)
         return hidden, llm
@@ -119,6 +159,8 @@ class AffectGPTFusion(nn.Module):
                 raise RuntimeError("Acoustic encoder is None but trying to use real-time mode.")  # :633-634, 695-696
             hidden = self.acoustic_encoder(audio, raw_audio)
         eng = self._eng(hidden.device)
+        if self.audio_fusion_type == "qformer":                                # :628-664
+            return hidden, eng.qformer_fuse("audio", audio_hidden=hidden)[1]
         llm = eng.audio_fuse(hidden, self.audio_fusion_type)
         llm = llm.unsqueeze(1).expand(-1, self.num_audio_query_token, -1)
         return hidden, llm
@@ -126,6 +168,8 @@ class AffectGPTFusion(nn.Module):
     @torch.no_grad()
     def encode_multi_merge(self, video_hidden_state, audio_hidden_state) -> Tuple[torch.Tensor, torch.Tensor]:
         eng = self._eng(video_hidden_state.device)
+        if self.multi_fusion_type == "qformer":                                # :848-881
+            return eng.qformer_fuse("multi", video_hidden=video_hidden_state, audio_hidden=audio_hidden_state)
         multi, llm = eng.multi_fuse(video_hidden_state, audio_hidden_state)
         return multi, llm.unsqueeze(1).expand(-1, self.num_multi_query_token, -1)
 

@@ -39,7 +39,10 @@ typedef struct agb_cfg {
   int32_t llm_dim;                /* projector output width (3584 = Qwen2.5-7B) */
   int32_t max_frames_per_chunk;   /* workspace sizing; 0 = default (512) */
   int32_t max_segments_per_chunk; /* workspace sizing; 0 = default (512) */
-  int32_t reserved[9];
+  int32_t qf_video_queries;       /* num_video_query_token when video_fusion_type == "qformer", else 0 (not built) */
+  int32_t qf_audio_queries;       /* num_audio_query_token when audio_fusion_type == "qformer", else 0 */
+  int32_t qf_multi_queries;       /* num_multi_query_token when multi_fusion_type == "qformer", else 0 */
+  int32_t reserved[6];
 } agb_cfg;
 
 enum { AGB_DTYPE_F32 = 0, AGB_DTYPE_U8 = 1, AGB_DTYPE_BF16 = 2 };
@@ -53,8 +56,9 @@ void agb_destroy(agb_ctx* ctx);
 /* text of the last error on this context (or the last global error when ctx is NULL) */
 const char* agb_last_error(agb_ctx* ctx);
 
-/* Weights.  `name` is "clip.<HF CLIPModel key>", "hubert.<HF HubertModel key>" or
- * "fusion.<AffectGPT ckpt['model'] key>"; fp32 device tensor; the context converts/packs into its
+/* Weights.  `name` is "clip.<HF CLIPModel key>", "hubert.<HF HubertModel key>", "fusion.<AffectGPT ckpt['model'] key>"
+ * (attention / mean heads) or "qf_video." / "qf_audio." / "qf_multi." + <ckpt key> (Q-Former variants: *_Qformer.bert.*,
+ * *_query_tokens, *position_embedding.weight and the 768-wide projectors); fp32 device tensor; the context converts/packs into its
  * own bf16 buffers (QKV concatenated, conv taps interleaved, weight-norm folded). */
 int agb_load_tensor(agb_ctx* ctx, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
                     void* stream);
@@ -77,6 +81,14 @@ int agb_audio_fuse(agb_ctx* ctx, const float* H, int B, int T, int fusion_type, 
 /* Hv: [B,Tv,768], Ha: [B,Ta,1024] -> multi_hidden [B,1024], llm [B,llm_dim] */
 int agb_multi_fuse(agb_ctx* ctx, const float* Hv, int Tv, const float* Ha, int Ta, int B, float* multi_hidden, float* llm,
                    void* stream);
+
+/* Q-Former variants (`*_fusion_type: qformer`): AffectGPT.encode_video_qformer affectgpt.py:420-468 (+ pre-extracted
+ * twin :563-580), encode_audio_qformer :628-664, encode_multi_qformer :848-881 over Qformer.py's 2-layer query
+ * transformer.  which: 0 video (Hv [B,Tv,768]), 1 audio (Ha [B,Ta,1024]), 2 multi (both).  hidden: [B,n_q,768] or NULL;
+ * llm: [B,n_q,llm_dim]. */
+enum { AGB_QF_VIDEO = 0, AGB_QF_AUDIO = 1, AGB_QF_MULTI = 2 };
+int agb_qformer_fuse(agb_ctx* ctx, int which, const float* Hv, int Tv, const float* Ha, int Ta, int B, float* hidden,
+                     float* llm, void* stream);
 
 /* Debug taps: after the next forward, copy the named intermediate (fp32 residual stream) to dst.
  * Names: "vit.embed", "vit.block<i>", "hubert.conv" (bf16 [n*100,512]), "hubert.featproj",

@@ -12,6 +12,7 @@ third-party imports that are not installed (decord, omegaconf, pytorchvideo, pef
 * ``models/affectgpt.py``: ``encode_{video,audio}_{attention,mean,qformer}``, ``encode_{video,audio}_merge``
   (pre-extracted twins), ``encode_multi_{attention,qformer}``, ``init_video_Qformer``
 * ``models/Qformer.py``: the 2-layer Q-Former those methods call
+* ``models/encoder.py``: ``CLIP_VIT_LARGE`` / ``HUBERT_LARGE`` (constructor + forward) on small random-init checkpoints
 
 Outputs: ``reference_sampling.json`` (integer contracts, bit-exact) and ``reference_fusion.npz`` (fp32 outputs for
 seeded inputs and seeded weights; weights are rebuilt from seeds by oracle/, not stored).
@@ -202,6 +203,51 @@ def fusion_fixtures():
     return out
 
 
+def encoder_fixtures():
+    """The reference's CLIP_VIT_LARGE / HUBERT_LARGE wrapper classes run on small random-init checkpoints (the oracle's
+    seeded builders, written to disk with save_pretrained): pins the preprocessing quirks (uint8 truncation, joint
+    waveform normalisation over the call, last-4-layer / time mean) against the reference's own forward code."""
+    from transformers import CLIPConfig, CLIPImageProcessor, CLIPModel, Wav2Vec2FeatureExtractor
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        vis, aud = os.path.join(d, "clip"), os.path.join(d, "hubert")
+        tower = R.build_clip_vision(num_layers=2, seed=1234)
+        cfg = CLIPConfig(vision_config=tower.config.to_dict(),
+                         text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2,
+                                          vocab_size=100, max_position_embeddings=16, projection_dim=768),
+                         projection_dim=768)
+        full = CLIPModel(cfg).eval()
+        missing, unexpected = full.load_state_dict(tower.state_dict(), strict=False)
+        assert not unexpected, unexpected
+        full.save_pretrained(vis)
+        CLIPImageProcessor(do_resize=True, size={"shortest_edge": 224}, do_center_crop=True,
+                           crop_size={"height": 224, "width": 224}, do_normalize=True, image_mean=list(R.CLIP_MEAN),
+                           image_std=list(R.CLIP_STD), do_convert_rgb=True).save_pretrained(vis)
+        hub = R.build_hubert(num_layers=3, feat_extract_norm="layer", seed=1234)
+        hub.save_pretrained(aud)
+        Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
+                                 return_attention_mask=True).save_pretrained(aud)
+        enc = L.load_encoders({"CLIP_VIT_LARGE": vis}, {"HUBERT_LARGE": aud})
+        clip = enc.CLIP_VIT_LARGE()
+        assert clip.hidden_size == 768
+        hubert = enc.HUBERT_LARGE()
+        assert hubert.hidden_size == 1024
+        with torch.no_grad():
+            frames = R.synth_frames(1, 2, seed=1) + 0.6                     # fractional part: exercises the uint8 truncation
+            out["clip2_frames_seed1_plus06_b1_t2"] = clip(None, frames).numpy()
+            audio = R.synth_audio(1, 2, seed=3)
+            out["hubert3_layer_audio_seed3_b1_t2"] = hubert(None, audio).numpy()
+            audio2 = R.synth_audio(2, 2, seed=5)                             # b = 2: joint normalisation over 4 segments
+            out["hubert3_layer_audio_seed5_b2_t2"] = hubert(None, audio2).numpy()
+            for key, got in (("clip2_frames_seed1_plus06_b1_t2", R.clip_vit_large_forward(tower, frames)),
+                             ("hubert3_layer_audio_seed3_b1_t2", R.hubert_large_forward(hub, audio)),
+                             ("hubert3_layer_audio_seed5_b2_t2", R.hubert_large_forward(hub, audio2))):
+                err = float((got - torch.from_numpy(out[key])).abs().max())
+                print(f"oracle vs reference {key}: max abs diff {err:.3e}")
+                assert err < 1e-4, (key, err)
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     samp = sampling_fixtures()
@@ -209,4 +255,6 @@ if __name__ == "__main__":
         json.dump(samp, f, separators=(",", ":"))
     fus = fusion_fixtures()
     np.savez_compressed(os.path.join(HERE, "reference_fusion.npz"), **fus)
-    print("wrote", len(samp), "sampling tables and", len(fus), "fusion tensors")
+    enc = encoder_fixtures()
+    np.savez_compressed(os.path.join(HERE, "reference_encoders.npz"), **enc)
+    print("wrote", len(samp), "sampling tables,", len(fus), "fusion tensors and", len(enc), "encoder outputs")

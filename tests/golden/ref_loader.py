@@ -198,3 +198,58 @@ def load_imagebind_data():
     mod.torchaudio = types.SimpleNamespace(load=FakeAudio.load, functional=torchaudio.functional,
                                            compliance=getattr(torchaudio, "compliance", None))
     return mod
+
+
+# ------------------------------------------------------------------------------------------ encoder wrappers (encoder.py)
+def load_encoders(path_visual: dict, path_audio: dict):
+    """The reference's registry encoder classes (``encoder.py``), constructed from checkpoints on disk.
+
+    Shims for transformers 4.49 -> 5.5 API drift, both outside the arithmetic of the path:
+    * ``AutoFeatureExtractor.from_pretrained`` no longer resolves CLIP: mapped to ``CLIPImageProcessor``;
+    * ``CLIPModel.get_image_features`` returns an output object in 5.x: unwrapped to ``pooler_output`` (the 4.49 tensor).
+    """
+    import transformers
+    for pkg in ("my_affectgpt", "my_affectgpt.models", "my_affectgpt.common", "my_affectgpt.models.ImageBind",
+                "my_affectgpt.models.ImageBind.models"):
+        sys.modules.setdefault(pkg, types.ModuleType(pkg))
+    du = _module("my_affectgpt.common.dist_utils", download_cached_file=None)
+    sys.modules["my_affectgpt.common"].dist_utils = du
+    _module("my_affectgpt.common.utils", is_url=lambda *_: False)
+    _module("my_affectgpt.common.logger", MetricLogger=object)
+
+    class BaseModel(nn.Module):
+        pass
+
+    class Blip2Base(BaseModel):
+        def maybe_autocast(self, dtype=torch.float16):
+            return contextlib.nullcontext()
+
+    _module("my_affectgpt.models.base_model", BaseModel=BaseModel)
+    sys.modules["my_affectgpt.models"].BaseModel = BaseModel
+    _module("my_affectgpt.models.blip2", Blip2Base=Blip2Base, disabled_train=lambda self, mode=True: self)
+    _module("my_affectgpt.models.eva_vit", create_eva_vit_g=None)
+    _module("my_affectgpt.models.Qformer", BertConfig=None, BertLMHeadModel=None)
+    ib = _module("my_affectgpt.models.ImageBind.models.imagebind_model", ImageBindModel=object, ModalityType=object)
+    sys.modules["my_affectgpt.models.ImageBind.models"].imagebind_model = ib
+    _module("config", PATH_TO_VISUAL=path_visual, PATH_TO_AUDIO=path_audio)
+    _load("my_affectgpt.common.registry", "my_affectgpt/common/registry.py")
+
+    class _AutoFeatureExtractor:
+        @staticmethod
+        def from_pretrained(model_dir, *a, **k):
+            return transformers.CLIPImageProcessor.from_pretrained(model_dir)
+
+    orig_afe = transformers.AutoFeatureExtractor
+    orig_gif = transformers.CLIPModel.get_image_features
+
+    def get_image_features(self, *a, **k):
+        out = orig_gif(self, *a, **k)
+        return out if isinstance(out, torch.Tensor) else out.pooler_output
+
+    transformers.AutoFeatureExtractor = _AutoFeatureExtractor
+    transformers.CLIPModel.get_image_features = get_image_features
+    try:
+        mod = _load("my_affectgpt.models.encoder", "my_affectgpt/models/encoder.py")
+    finally:
+        transformers.AutoFeatureExtractor = orig_afe
+    return mod

@@ -1,0 +1,104 @@
+"""CUDA path vs fixtures produced by the REFERENCE's own code (tests/golden/make_reference_golden.py): encoder wrapper
+classes, attention / mean heads, and the three Q-Former fusion variants.  Everything goes through the
+reference-shaped Python surface and therefore through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qformer as OQ
+from oracle import reference_path as R
+from tests.gpu_util import gate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FUS = np.load(os.path.join(GOLD, "reference_fusion.npz"))
+ENC = np.load(os.path.join(GOLD, "reference_encoders.npz"))
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(7)
+    frame_h = torch.randn(3, 8, 768, generator=g)
+    face_h = torch.randn(3, 8, 768, generator=g)
+    audio_h = torch.randn(3, 8, 1024, generator=g)
+    frame_vec = torch.randn(3, 768, generator=g)
+    return frame_h.to(DEV), face_h.to(DEV), audio_h.to(DEV), frame_vec.to(DEV)
+
+
+def _close(got, key, tol):
+    want = torch.from_numpy(FUS[key])
+    assert tuple(got.shape) == tuple(want.shape), (key, tuple(got.shape), tuple(want.shape))
+    err = float((got.float().cpu() - want).abs().max()) / max(float(want.abs().max()), 1e-12)
+    print(f"[ref-golden] {key}: rel err {err:.2e}")
+    assert err < tol, (key, err)
+
+
+def test_encoder_classes_match_reference_encoder_py():
+    """reference_encoders.npz = CLIP_VIT_LARGE / HUBERT_LARGE of the reference's encoder.py on the oracle's small seeded
+    checkpoints; here the drop-in classes of the same names, fed the same state dicts."""
+    import affectgpt_b200 as agb
+    clip = R.build_clip_vision(num_layers=2, seed=1234)
+    hub = R.build_hubert(num_layers=3, feat_extract_norm="layer", seed=1234)
+    model = agb.build_path(clip.state_dict(), hub.state_dict(), R.build_fusion_state(seed=1234), device=DEV, vit_layers=2,
+                           hubert_layers=3, norm_scope="batch")
+    got = model.visual_encoder(None, (R.synth_frames(1, 2, seed=1) + 0.6).to(DEV))
+    gate(got, torch.from_numpy(ENC["clip2_frames_seed1_plus06_b1_t2"]), "reference CLIP_VIT_LARGE.forward")
+    for key, audio in (("hubert3_layer_audio_seed3_b1_t2", R.synth_audio(1, 2, seed=3)),
+                       ("hubert3_layer_audio_seed5_b2_t2", R.synth_audio(2, 2, seed=5))):
+        got = model.acoustic_encoder(None, audio.to(DEV))           # norm_scope="batch": statistics over the call (F3)
+        gate(got, torch.from_numpy(ENC[key]), "reference HUBERT_LARGE.forward " + key)
+
+
+def test_attention_and_mean_heads_match_reference_methods():
+    import affectgpt_b200 as agb
+    frame_h, face_h, audio_h, frame_vec = _inputs()
+    st = R.build_fusion_state(seed=1234)
+    m = agb.AffectGPTFusion(lambda a, b: frame_h, lambda a, b: audio_h)
+    m.load_state_dict(st)
+    _close(m.encode_video_merge(None, frame_h)[1], "att_video_merge_realtime_llm", 1e-4)
+    _close(m.encode_video_merge(face_h, None, is_preextracted=True)[1], "att_video_pre3d_llm", 1e-4)
+    h, l = m.encode_video_merge(frame_vec, None, is_preextracted=True)
+    _close(l, "att_video_pre2d_llm", 1e-4)
+    _close(h, "att_video_pre2d_hidden", 1e-6)
+    _close(m.encode_audio_merge(None, audio_h)[1], "att_audio_realtime_llm", 1e-4)
+    _close(m.encode_audio_merge(audio_h, None, is_preextracted=True)[1], "att_audio_pre_llm", 1e-4)
+    mh, ml = m.encode_multi_merge(face_h, audio_h)
+    _close(mh, "att_multi_hidden", 1e-4)
+    _close(ml, "att_multi_llm", 1e-4)
+    mm = agb.AffectGPTFusion(lambda a, b: frame_h, lambda a, b: audio_h, video_fusion_type="mean", audio_fusion_type="mean")
+    mm.load_state_dict(st)
+    _close(mm.encode_video_merge(None, frame_h)[1], "mean_video_realtime_llm", 1e-4)
+    _close(mm.encode_video_merge(face_h, None, is_preextracted=True)[1], "mean_video_pre3d_llm", 1e-4)
+    _close(mm.encode_audio_merge(None, audio_h)[1], "mean_audio_realtime_llm", 1e-4)
+    _close(mm.encode_audio_merge(audio_h, None, is_preextracted=True)[1], "mean_audio_pre_llm", 1e-4)
+
+
+def test_qformer_variants_match_reference_qformer_py():
+    import affectgpt_b200 as agb
+    frame_h, face_h, audio_h, frame_vec = _inputs()
+    qs = OQ.fusion_qformer_state(seed=4321, n_query=4)
+    m = agb.AffectGPTFusion(lambda a, b: frame_h, lambda a, b: audio_h, video_fusion_type="qformer",
+                            audio_fusion_type="qformer", multi_fusion_type="qformer", num_video_query_token=4,
+                            num_audio_query_token=4, num_multi_query_token=4)
+    m.load_state_dict(qs)
+    h, l = m.encode_video_merge(None, frame_h)
+    assert torch.equal(h, frame_h)
+    _close(l, "qf_video_realtime_llm", 2e-4)
+    _close(m.encode_video_merge(face_h, None, is_preextracted=True)[1], "qf_video_pre3d_llm", 2e-4)
+    _close(m.encode_video_merge(frame_vec, None, is_preextracted=True)[1], "qf_video_pre2d_llm", 2e-4)
+    _close(m.encode_audio_merge(None, audio_h)[1], "qf_audio_realtime_llm", 2e-4)
+    mh, ml = m.encode_multi_merge(face_h, audio_h)
+    _close(mh, "qf_multi_hidden", 2e-4)
+    _close(ml, "qf_multi_llm", 2e-4)
+    # a mixed model: Q-Former for the multi token only, shipping attention heads elsewhere
+    st = dict(R.build_fusion_state(seed=1234))
+    st.update({k: v for k, v in qs.items() if k.startswith("multi_")})
+    mix = agb.AffectGPTFusion(lambda a, b: frame_h, lambda a, b: audio_h, multi_fusion_type="qformer",
+                              num_multi_query_token=4)
+    mix.load_state_dict(st)
+    _close(mix.encode_video_merge(None, frame_h)[1], "att_video_merge_realtime_llm", 1e-4)
+    _close(mix.encode_multi_merge(face_h, audio_h)[1], "qf_multi_llm", 2e-4)
+    with pytest.raises(RuntimeError):                       # 300 tokens exceed multi_position_embedding's 264 rows
+        mix.encode_multi_merge(torch.zeros(1, 292, 768, device=DEV), torch.zeros(1, 8, 1024, device=DEV))

@@ -59,8 +59,10 @@ def test_model_errors_match_reference():
         m.encode_audio_merge(None, torch.zeros(1, 8, 1, 32000))
     with pytest.raises(ValueError):                                  # :559-560
         m.encode_video_merge(torch.zeros(1, 2, 3, 4), None, is_preextracted=True)
-    with pytest.raises(NotImplementedError):
-        agb.AffectGPTFusion(None, None, video_fusion_type="qformer")
+    with pytest.raises(ValueError):
+        agb.AffectGPTFusion(None, None, video_fusion_type="transformer")
+    qf = agb.AffectGPTFusion(None, None, video_fusion_type="qformer", num_video_query_token=4)     # all three variants exist
+    assert qf._engine_cfg["qf_video_queries"] == 4 and "video_attention_mlp" not in qf._needed_heads()
     missing, unexpected = m.load_state_dict({"llama_model.x": torch.zeros(1), "fc_att.weight": torch.zeros(2, 1024)})
     assert "fc_att.bias" in missing and unexpected == ["llama_model.x"]
 

@@ -112,3 +112,17 @@ def test_oracle_qformer_variants_match_reference():
         mh, ml = OQ.encode_multi_qformer(qs, face_h, audio_h)
         _close(mh, "qf_multi_hidden")
         _close(ml, "qf_multi_llm")
+
+
+def test_oracle_encoder_wrappers_match_reference_classes():
+    """reference_encoders.npz = outputs of the reference's CLIP_VIT_LARGE / HUBERT_LARGE classes (encoder.py) on the
+    oracle's small seeded checkpoints: pins uint8 truncation, call-wide waveform normalisation, last-4 / time mean."""
+    enc = np.load(os.path.join(HERE, "golden", "reference_encoders.npz"))
+    tower = R.build_clip_vision(num_layers=2, seed=1234)
+    got = R.clip_vit_large_forward(tower, R.synth_frames(1, 2, seed=1) + 0.6)
+    assert float((got - torch.from_numpy(enc["clip2_frames_seed1_plus06_b1_t2"])).abs().max()) < 1e-4
+    hub = R.build_hubert(num_layers=3, feat_extract_norm="layer", seed=1234)
+    for key, audio in (("hubert3_layer_audio_seed3_b1_t2", R.synth_audio(1, 2, seed=3)),
+                       ("hubert3_layer_audio_seed5_b2_t2", R.synth_audio(2, 2, seed=5))):
+        got = R.hubert_large_forward(hub, audio)
+        assert float((got - torch.from_numpy(enc[key])).abs().max()) < 1e-4, key
