@@ -822,6 +822,17 @@ int agb_qformer_fuse(agb_ctx* ctx, int which, const float* Hv, int Tv, const flo
   return r ? fail(ctx, r) : 0;
 }
 
+int agb_stage_faces(const void* faces_u8, int64_t n_src, int h, int w, const int32_t* idx, int T, void* out_u8, void* stream) {
+  return stage_faces_u8(static_cast<const uint8_t*>(faces_u8), n_src, h, w, idx, T, static_cast<uint8_t*>(out_u8),
+                        static_cast<cudaStream_t>(stream));
+}
+
+int agb_stage_audio(const float* wav, int ch, int64_t n, const int64_t* starts, int clips, int clip_len, float* out,
+                    void* stream) {
+  return stage_audio_f32(wav, ch, n, reinterpret_cast<const long long*>(starts), clips, clip_len, out,
+                         static_cast<cudaStream_t>(stream));
+}
+
 // ---- kernel-level entry points ---------------------------------------------------------------
 int agb_op_gemm(int a_mode, int act, const void* A, int64_t lda, const void* W, int M, int N, int K, const float* bias,
                 const float* res, int64_t ld_res, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, int nseq,

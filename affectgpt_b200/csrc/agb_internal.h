@@ -158,6 +158,14 @@ int gelu_erf_f32_inplace(float* x, int64_t n, cudaStream_t s);
 int mha12x64_f32(const float* q, const float* k, const float* v, int B, int Tq, int Tk, float* out, cudaStream_t s);
 int qformer_forward_f32(const QFormerW& W, const float* enc, int B, int T, QFormerWs& ws, cudaStream_t s);
 
+// staging.cu ---------------------------------------------------------------------------------
+// faces [n_src,h,w,3] u8 -> out [T,3,224,224] u8: cv2.resize(INTER_LINEAR) of the crops selected by idx_dev, bit-exact
+int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int* idx_dev, int T, uint8_t* out,
+                   cudaStream_t s);
+// wav [ch,n] f32 -> out [clips,clip_len]: mono mix (2 channels: mean), zero padding, slices at starts_dev
+int stage_audio_f32(const float* wav, int ch, int64_t n, const long long* starts_dev, int clips, int clip_len, float* out,
+                    cudaStream_t s);
+
 // pack.cu ------------------------------------------------------------------------------------
 int convert_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
 // dst[r, c] (row stride ld_dst) = src[r, c] for r<rows, c<cols; zero-fills c in [cols, cols_pad)

@@ -1,0 +1,96 @@
+// Input staging on the GPU: the two steps that sit between the decoders and the encoders and that the reference runs
+// on the CPU for every sample.
+//
+//  * face crops: ``load_face`` (A/my_affectgpt/processors/video_processor.py:262-296) = np.load of the OpenFace crop
+//    stack [N,h,w,3] u8, ``cv2.resize(face, (224, 224))`` of EVERY crop, then the uniform index rule.  Here only the
+//    sampled crops are resized, straight into the planar u8 layout the ViT patchify kernel reads.  The arithmetic is
+//    OpenCV's fixed-point INTER_LINEAR for 8-bit images, bit for bit (resize.cpp: 11-bit coefficients from float
+//    source coordinates, horizontal pass in 32-bit, vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2 >> 2;
+//    horizontal border taps reset the weight to (2048, 0), vertical border taps keep their weights and clamp the row).
+//    Verified against cv2 itself through the reference's own load_face: tests/golden/reference_face_resize.npz.
+//  * audio: ``load_audio`` (A/my_affectgpt/models/ImageBind/data.py:188-212) after decode/resample: stereo -> mean,
+//    zero padding to 2 s, eight [start, start + 32000) slices.  The slice starts are computed on the host in exact
+//    rational arithmetic (affectgpt_b200/sampling.py); the kernel is the gather.
+#include "agb_internal.h"
+
+namespace agb {
+
+namespace {
+
+struct Tap {
+  int i0, i1, a0, a1;
+};
+
+// OpenCV resize.cpp, INTER_LINEAR, fixed point: source tap and 11-bit weights of destination coordinate d
+__device__ __forceinline__ Tap cv_linear_tap(int d, int src, int dst, bool reset_border_weight) {
+  const double inv_scale = (double)dst / (double)src;
+  const double scale = 1.0 / inv_scale;
+  // (float)((d + 0.5) * scale - 0.5) with separately rounded multiply and subtract (no FMA contraction)
+  float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (reset_border_weight) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  Tap t;
+  t.i0 = min(max(s, 0), src - 1);
+  t.i1 = min(max(s + 1, 0), src - 1);
+  t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));    // saturate_cast<short>(cvRound(...)); |v| <= 2048
+  t.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+// grid (224 rows, T frames), block 224: out[t, c, dy, dx] <- faces[idx[t]] resized
+__global__ void __launch_bounds__(224) face_resize_kernel(const uint8_t* __restrict__ faces, int h, int w,
+                                                         const int* __restrict__ idx, uint8_t* __restrict__ out) {
+  const int dy = blockIdx.x, t = blockIdx.y, dx = threadIdx.x;
+  const uint8_t* img = faces + (long long)idx[t] * h * w * 3;
+  const Tap ty = cv_linear_tap(dy, h, 224, false);
+  const Tap tx = cv_linear_tap(dx, w, 224, true);
+  const uint8_t* r0 = img + (long long)ty.i0 * w * 3;
+  const uint8_t* r1 = img + (long long)ty.i1 * w * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int s0 = r0[tx.i0 * 3 + c] * tx.a0 + r0[tx.i1 * 3 + c] * tx.a1;     // horizontal pass, scaled by 2^11
+    const int s1 = r1[tx.i0 * 3 + c] * tx.a0 + r1[tx.i1 * 3 + c] * tx.a1;
+    const int v = (((ty.a0 * (s0 >> 4)) >> 16) + ((ty.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    out[(((long long)t * 3 + c) * 224 + dy) * 224 + dx] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// out[clip, i] = sample (start[clip] + i) of the mono mix, zero beyond the end of the waveform
+__global__ void __launch_bounds__(256) audio_gather_kernel(const float* __restrict__ wav, int ch, long long n,
+                                                          const long long* __restrict__ starts, int clip_len,
+                                                          float* __restrict__ out) {
+  const int clip = blockIdx.y;
+  const long long s0 = starts[clip];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < clip_len; i += gridDim.x * 256) {
+    const long long p = s0 + i;
+    float v = 0.f;
+    if (p >= 0 && p < n) v = (ch == 2) ? (wav[p] + wav[n + p]) * 0.5f : wav[p];    // data.py:190-191 (two channels only)
+    out[(long long)clip * clip_len + i] = v;
+  }
+}
+
+}  // namespace
+
+int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int* idx_dev, int T, uint8_t* out,
+                   cudaStream_t s) {
+  AGB_REQUIRE(faces && idx_dev && out && n_src > 0 && h > 0 && w > 0 && T > 0, "stage_faces: bad arguments");
+  LaunchTimer timer(PROF_FRONTEND, 0.0, (double)T * (4.0 * 3 * 224 * 224 + 3.0 * 224 * 224), s);
+  face_resize_kernel<<<dim3(224, T), 224, 0, s>>>(faces, h, w, idx_dev, out);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+int stage_audio_f32(const float* wav, int ch, int64_t n, const long long* starts_dev, int clips, int clip_len, float* out,
+                    cudaStream_t s) {
+  AGB_REQUIRE(wav && starts_dev && out && ch >= 1 && n >= 0 && clips > 0 && clip_len > 0, "stage_audio: bad arguments");
+  LaunchTimer timer(PROF_FRONTEND, 0.0, (double)clips * clip_len * 4.0 * (ch == 2 ? 3.0 : 2.0), s);
+  audio_gather_kernel<<<dim3(32, clips), 256, 0, s>>>(wav, ch, n, starts_dev, clip_len, out);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace agb

@@ -90,6 +90,15 @@ enum { AGB_QF_VIDEO = 0, AGB_QF_AUDIO = 1, AGB_QF_MULTI = 2 };
 int agb_qformer_fuse(agb_ctx* ctx, int which, const float* Hv, int Tv, const float* Ha, int Ta, int B, float* hidden,
                      float* llm, void* stream);
 
+/* Input staging (device pointers throughout).
+ * agb_stage_faces: load_face, video_processor.py:262-296 - faces [n_src,h,w,3] u8 (OpenFace crop stack), idx [T] int32
+ *   (uniform index rule, computed by the host) -> out [T,3,224,224] u8 = cv2.resize(face, (224,224)) bit for bit.
+ * agb_stage_audio: load_audio, ImageBind/data.py:188-212 after decode/resample - wav [ch,n] f32, starts [clips] int64
+ *   (host, exact rational arithmetic) -> out [clips,clip_len] f32: two channels are averaged, samples past n are 0. */
+int agb_stage_faces(const void* faces_u8, int64_t n_src, int h, int w, const int32_t* idx, int T, void* out_u8, void* stream);
+int agb_stage_audio(const float* wav, int ch, int64_t n, const int64_t* starts, int clips, int clip_len, float* out,
+                    void* stream);
+
 /* Debug taps: after the next forward, copy the named intermediate (fp32 residual stream) to dst.
  * Names: "vit.embed", "vit.block<i>", "hubert.conv" (bf16 [n*100,512]), "hubert.featproj",
  * "hubert.posconv", "hubert.block<i>".  dst == NULL removes the tap. */

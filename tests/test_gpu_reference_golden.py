@@ -102,3 +102,45 @@ def test_qformer_variants_match_reference_qformer_py():
     _close(mix.encode_multi_merge(face_h, audio_h)[1], "qf_multi_llm", 2e-4)
     with pytest.raises(RuntimeError):                       # 300 tokens exceed multi_position_embedding's 264 rows
         mix.encode_multi_merge(torch.zeros(1, 292, 768, device=DEV), torch.zeros(1, 8, 1024, device=DEV))
+
+
+def test_face_staging_is_bit_exact_with_cv2_through_reference_load_face():
+    """reference_face_resize.npz = the reference's load_face (np.load -> cv2.resize each crop -> sample) on random crops."""
+    from affectgpt_b200 import staging
+    d = np.load(os.path.join(GOLD, "reference_face_resize.npz"))
+    got = staging.load_face(d["faces"], n_frms=3, device=DEV)               # [3(c), 3(t), 224, 224] float
+    assert got.dtype == torch.float32 and tuple(got.shape) == (3, 3, 224, 224)
+    assert torch.equal(got.cpu().to(torch.uint8), torch.from_numpy(d["resized"]))
+    got8 = staging.load_face(d["faces"], n_frms=8, device=DEV)              # 3 crops -> indices [0,1,2,2,2,2,2,2]
+    assert torch.equal(got8[:, 3], got8[:, 2]) and torch.equal(got8[:, :3], got)
+
+
+@pytest.mark.parametrize("h,w", [(224, 224), (112, 112), (448, 300), (31, 17), (223, 225), (1, 1), (2, 3), (720, 1280)])
+def test_face_staging_matches_cv2_resize(h, w):
+    cv2 = pytest.importorskip("cv2")
+    from affectgpt_b200 import staging
+    rng = np.random.default_rng(h * 1000 + w)
+    faces = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+    got = staging.stage_faces(faces, [1, 0, 1], device=DEV).cpu().numpy()
+    for t, i in enumerate([1, 0, 1]):
+        want = cv2.resize(faces[i], (224, 224)).transpose(2, 0, 1)
+        assert np.array_equal(got[t], want), (h, w, t, int(np.abs(got[t].astype(int) - want.astype(int)).max()))
+
+
+def test_audio_staging_matches_reference_load_audio_slices():
+    import json
+    from affectgpt_b200 import sampling, staging
+    with open(os.path.join(GOLD, "reference_sampling.json")) as f:
+        cases = json.load(f)["audio"]
+    for case in cases:
+        n, ch = case["n"], case["channels"]
+        base = torch.arange(n, dtype=torch.float32) + 1.0
+        wav = torch.stack([base, base]) if ch == 2 else base[None]
+        got = staging.stage_audio(wav, device=DEV).cpu()
+        assert tuple(got.shape) == (8, 1, 32000)
+        assert [int(x) - 1 for x in got[:, 0, 0]] == case["starts"], case
+        assert [int(x) - 1 for x in got[:, 0, -1]] == case["last_sample"], case
+        assert torch.equal(got, sampling.segment_audio(wav))                     # whole tensor, bit for bit
+    g = torch.Generator().manual_seed(3)
+    wav = torch.randn(2, 70001, generator=g)
+    assert torch.equal(staging.stage_audio(wav, device=DEV).cpu(), sampling.segment_audio(wav))   # true stereo mix-down
