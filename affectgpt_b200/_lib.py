@@ -43,6 +43,8 @@ SIGNATURES = {
     "agb_video_fuse": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "agb_audio_fuse": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "agb_multi_fuse": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "agb_splice_tokens": (_i, [_vp, _i, _vp, _i, _i, _i, _i, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                C.POINTER(_vp), _vp, _vp]),
     "agb_stage_faces": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp, _vp]),
     "agb_stage_audio": (_i, [_vp, _i, _i64, _vp, _i, _i, _vp, _vp]),
     "agb_qformer_fuse": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

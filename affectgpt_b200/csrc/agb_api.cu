@@ -822,6 +822,14 @@ int agb_qformer_fuse(agb_ctx* ctx, int which, const float* Hv, int Tv, const flo
   return r ? fail(ctx, r) : 0;
 }
 
+int agb_splice_tokens(void* embeds, int dtype, const int64_t* input_ids, int B, int L, int D, int n_mod,
+                      const int64_t* token_ids, const int32_t* n_query, const float* const* mod_embeds, int32_t* status,
+                      void* stream) {
+  return splice_tokens(embeds, dtype, reinterpret_cast<const long long*>(input_ids), B, L, D, n_mod,
+                       reinterpret_cast<const long long*>(token_ids), n_query, mod_embeds, status,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int agb_stage_faces(const void* faces_u8, int64_t n_src, int h, int w, const int32_t* idx, int T, void* out_u8, void* stream) {
   return stage_faces_u8(static_cast<const uint8_t*>(faces_u8), n_src, h, w, idx, T, static_cast<uint8_t*>(out_u8),
                         static_cast<cudaStream_t>(stream));

@@ -166,6 +166,12 @@ int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int*
 int stage_audio_f32(const float* wav, int ch, int64_t n, const long long* starts_dev, int clips, int clip_len, float* out,
                     cudaStream_t s);
 
+// splice.cu ----------------------------------------------------------------------------------
+// in-place on embeds [B,L,D] (fp32 or bf16); status [B,n_mod,3] = {count, first position or -1, consecutive}
+int splice_tokens(void* embeds_inout, int dtype, const long long* ids, int B, int L, int D, int n_mod,
+                  const long long* token_ids, const int* n_query, const float* const* mod_embeds, int* status_dev,
+                  cudaStream_t s);
+
 // pack.cu ------------------------------------------------------------------------------------
 int convert_f32_to_bf16(const float* src, bf16* dst, int64_t n, cudaStream_t s);
 // dst[r, c] (row stride ld_dst) = src[r, c] for r<rows, c<cols; zero-fills c in [cols, cols_pad)

@@ -99,6 +99,15 @@ int agb_stage_faces(const void* faces_u8, int64_t n_src, int h, int w, const int
 int agb_stage_audio(const float* wav, int ch, int64_t n, const int64_t* starts, int clips, int clip_len, float* out,
                     void* stream);
 
+/* Token splice (AffectGPT.forward, affectgpt.py:956-1009): in place on embeds [B,L,D] (AGB_DTYPE_F32 / AGB_DTYPE_BF16).
+ * input_ids [B,L] int64 (device); token_ids / n_query / mod_embeds are HOST arrays of n_mod (<= 8) entries, mod_embeds[i]
+ * a device pointer to [B,n_query[i],D] fp32 or NULL.  A modality is spliced into a sample when its placeholder occurs
+ * exactly n_query times, consecutively; status (device, [B,n_mod,3] int32 = count, first position, consecutive flag)
+ * lets the caller raise the reference's ValueErrors for the other cases. */
+int agb_splice_tokens(void* embeds, int dtype, const int64_t* input_ids, int B, int L, int D, int n_mod,
+                      const int64_t* token_ids, const int32_t* n_query, const float* const* mod_embeds, int32_t* status,
+                      void* stream);
+
 /* Debug taps: after the next forward, copy the named intermediate (fp32 residual stream) to dst.
  * Names: "vit.embed", "vit.block<i>", "hubert.conv" (bf16 [n*100,512]), "hubert.featproj",
  * "hubert.posconv", "hubert.block<i>".  dst == NULL removes the tap. */

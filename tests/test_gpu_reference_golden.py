@@ -144,3 +144,51 @@ def test_audio_staging_matches_reference_load_audio_slices():
     g = torch.Generator().manual_seed(3)
     wav = torch.randn(2, 70001, generator=g)
     assert torch.equal(staging.stage_audio(wav, device=DEV).cpu(), sampling.segment_audio(wav))   # true stereo mix-down
+
+
+TOK = {"frame": 1001, "face": 1002, "audio": 1003, "multi": 1004, "image": 1005}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("nq", [{"frame": 1, "face": 1, "audio": 1, "multi": 1}, {"frame": 4, "face": 4, "audio": 2, "multi": 3}])
+def test_gpu_splice_matches_reference_loop(nq, dtype):
+    """oracle.sampling.splice is the literal per-sample restatement of affectgpt.py:956-1009."""
+    from affectgpt_b200 import splice as P
+    from oracle import sampling as O
+    g = torch.Generator().manual_seed(0)
+    b, L, D = 5, 300, 3584
+    ids = torch.randint(5, 900, (b, L), generator=g)
+    for i in range(b - 1):                                   # the last sample carries no placeholder at all
+        pos = 3 + 7 * i
+        for name in ["multi", "audio", "face", "frame"]:     # base_dataset.py:882-889 prompt order
+            ids[i, pos:pos + nq[name]] = TOK[name]
+            pos += nq[name] + 2 + i
+    emb = torch.randn(b, L, D, generator=g).to(dtype)
+    feats = {k: torch.randn(b, nq[k], D, generator=g) for k in nq}
+    want = torch.stack([O.splice(emb[i:i + 1].float(), ids[i:i + 1], TOK, nq, {k: v[i:i + 1] for k, v in feats.items()})[0]
+                        for i in range(b)])
+    got = P.splice_tokens(emb.to(DEV), ids.to(DEV), TOK, nq, {k: v.to(DEV) for k, v in feats.items()})
+    assert got.dtype == dtype
+    assert torch.equal(got.float().cpu(), want.to(dtype).float())
+    assert torch.equal(got[-1].cpu(), emb[-1])
+
+
+def test_gpu_splice_raises_like_reference():
+    from affectgpt_b200 import splice as P
+    nq = {"frame": 2, "audio": 1}
+    emb = torch.zeros(2, 16, 8, device=DEV)
+    feats = {"frame": torch.ones(2, 2, 8, device=DEV), "audio": torch.ones(2, 1, 8, device=DEV)}
+    ids = torch.full((2, 16), 7)
+    ids[1, 3] = TOK["frame"]                                 # count != n_query in one sample
+    with pytest.raises(ValueError, match="number of audio patch tokens"):
+        P.splice_tokens(emb, ids, TOK, nq, feats)
+    ids[1, 9] = TOK["frame"]                                 # right count, not consecutive
+    with pytest.raises(ValueError, match="consecutive"):
+        P.splice_tokens(emb, ids, TOK, nq, feats)
+    ids2 = torch.full((2, 16), 7)
+    ids2[0, 5] = TOK["audio"]
+    with pytest.raises(AssertionError):                      # placeholder present, embeds missing
+        P.splice_tokens(emb, ids2, TOK, nq, {"frame": feats["frame"]})
+    ids3 = torch.full((2, 16), 7)
+    out = P.splice_tokens(emb, ids3, TOK, nq, feats)         # no placeholders: identity
+    assert torch.equal(out, emb)

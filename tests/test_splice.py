@@ -25,9 +25,6 @@ def test_splice_matches_reference_order(nq):
     ids = _prompt(b, L, ["multi", "audio", "face", "frame"], nq, g)     # base_dataset.py:882-889 prompt order
     emb = torch.randn(b, L, D, generator=g)
     feats = {k: torch.randn(b, nq[k], D, generator=g) for k in nq}
-    want = O.splice(emb, ids, TOK, nq, feats)
-    got = P.splice_tokens(emb, ids, TOK, nq, feats)
-    assert torch.equal(got, want)
     pos = P.placeholder_positions(ids, TOK, nq, list(feats))
     for i in range(b):
         ref = O.splice_positions(ids[i].tolist(), TOK, nq, list(feats))
@@ -41,21 +38,29 @@ def test_splice_errors_like_reference():
     emb = torch.zeros(1, 16, 4)
     feats = {"frame": torch.zeros(1, 2, 4), "audio": torch.zeros(1, 1, 4)}
     with pytest.raises(ValueError):
-        P.splice_tokens(emb, ids, TOK, nq, feats)
+        P.placeholder_positions(ids, TOK, nq, list(feats))
     with pytest.raises(ValueError):
         O.splice(emb, ids, TOK, nq, feats)
     ids[0, 9] = TOK["frame"]                                # right count, not consecutive
     with pytest.raises(ValueError):
-        P.splice_tokens(emb, ids, TOK, nq, feats)
+        P.placeholder_positions(ids, TOK, nq, list(feats))
     with pytest.raises(ValueError):
         O.splice(emb, ids, TOK, nq, feats)
     ids2 = torch.full((1, 16), 7)
     ids2[0, 5] = TOK["audio"]
     with pytest.raises(AssertionError):                     # placeholder present, embeds missing
-        P.splice_tokens(emb, ids2, TOK, nq, {"frame": feats["frame"]})
+        P.placeholder_positions(ids2, TOK, nq, ["frame"])
 
 
-def test_no_placeholders_is_identity():
-    emb = torch.randn(2, 8, 4)
-    ids = torch.full((2, 8), 3)
-    assert torch.equal(P.splice_tokens(emb, ids, TOK, {"frame": 1}, {"frame": torch.zeros(2, 1, 4)}), emb)
+def test_per_sample_semantics_and_no_cpu_fallback():
+    """The reference loops per sample (:968-1005): a sample without a placeholder is left alone even when another sample
+    of the batch carries it."""
+    nq = {"frame": 2}
+    ids = torch.full((2, 12), 7)
+    ids[1, 4:6] = TOK["frame"]
+    pos = P.placeholder_positions(ids, TOK, nq, ["frame"])
+    assert pos["frame"].tolist() == [-1, 4]
+    assert O.splice_positions(ids[0].tolist(), TOK, nq, ["frame"]) == {}
+    assert O.splice_positions(ids[1].tolist(), TOK, nq, ["frame"]) == {"frame": 4}
+    with pytest.raises(RuntimeError):                       # the copy itself is a CUDA kernel: no CPU path
+        P.splice_tokens(torch.zeros(2, 12, 4), ids, TOK, nq, {"frame": torch.zeros(2, 2, 4)})
