@@ -1,0 +1,361 @@
+"""Pre-extracted feature sweep: drop-in for the reference's ``extract_multimodal_features_precompute.py``.
+
+Same command line (``--dataset --modality --video_root --face_root --audio_root --sample_list/--csv_path --save_root
+--visual_encoder --acoustic_encoder --frame_n_frms --frame_sampling --clips_per_video --skip-multi-preextract
+--mer-factory-output --device --quiet``), same on-disk layout and semantics
+(A/extract_multimodal_features_precompute.py:823-849, 892-1024, 1054-1098):
+
+    <save_root>/<dataset>/frame_<visual>_<sampling>_<n>frms/<name>.npy      fp32 [n, 768]
+    <save_root>/<dataset>/face_<visual>_8frms/<name>.npy                    fp32 [8, 768]     (always 8 frames, uniform)
+    <save_root>/<dataset>/audio_<acoustic>_<clips>clips/<name>.npy          fp32 [clips, 1024]
+    <save_root>/<dataset>/multi_<visual>_<acoustic>_complete/<name>.npy     fp32 [1024]
+
+* a file that already exists is skipped (resume), a failed sample is skipped, except audio, which is zero-filled
+  ``[clips, 1024]`` when the wav is missing or its processing fails (:965-968, 970-975);
+* every exception inside an ``extract_*`` call is swallowed and turned into ``None`` (:227-229, 587-589, 610-612);
+* the loaders the directories are read by: A/my_affectgpt/datasets/datasets/base_dataset.py:392-405, 481-492, 520-531.
+
+What differs is where the work runs: frames, face crops and audio segments are staged on the GPU (``staging``), the
+encoders and fusion heads are the sm_100a kernels behind the C ABI, and samples are batched per launch.  Under
+``torchrun`` each rank takes samples ``rank::world_size`` and writes its own files - no collective.
+Decoding (mp4 / wav) is outside the path: videos are read with decord when it is installed, else OpenCV, else a
+pre-decoded ``<video_root>/<name>.npy`` uint8 stack ``[N,h,w,3]`` (RGB); wavs with scipy.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import sampling, staging
+from .parallel import shard_indices
+
+DATASETS = ['mer2023', 'mer2024', 'mercaptionplus', 'cmumosei', 'cmumosi', 'iemocapfour', 'meld', 'sims', 'simsv2']
+
+
+# --------------------------------------------------------------------------------------------- decoding (host, out of path)
+def _au_info(video_name: Optional[str], mer_factory_output: Optional[str]) -> Optional[dict]:
+    """video_processor.py:29-56 (_load_au_info)."""
+    import json
+    if not video_name or not mer_factory_output:
+        return None
+    path = os.path.join(mer_factory_output, video_name, f"{video_name}_au_analysis.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        with open(path, "r", encoding="utf-8") as f:
+            return json.load(f).get("au_info")
+    except Exception:
+        return None
+
+
+def frame_indices(vlen: int, n_frms: int, sampling_mode: str, video_name: Optional[str] = None,
+                  mer_factory_output: Optional[str] = None) -> List[int]:
+    """The index rule of load_video (video_processor.py:204-244)."""
+    if sampling_mode == "uniform":
+        return sampling.uniform_frame_indices(vlen, n_frms)
+    if sampling_mode == "headtail":
+        return sampling.headtail_frame_indices(vlen, n_frms)
+    if sampling_mode == "emotion_peak":
+        return sampling.emotion_peak_frame_indices(vlen, _au_info(video_name, mer_factory_output), n_frms)
+    raise NotImplementedError(sampling_mode)
+
+
+def read_video_frames(video_path: str, pick: Callable[[int], List[int]]) -> np.ndarray:
+    """-> uint8 [T,224,224,3] RGB frames ``pick(vlen)`` of the video, resized to 224x224 by the decoder."""
+    stack = os.path.splitext(video_path)[0] + ".npy"
+    if not os.path.exists(video_path) and os.path.exists(stack):
+        frames = np.load(stack, mmap_mode="r")
+        idx = pick(len(frames))
+        sel = np.ascontiguousarray(frames[idx])
+        if sel.shape[1:3] != (224, 224):
+            import cv2
+            sel = np.stack([cv2.resize(f, (224, 224)) for f in sel])
+        return sel
+    try:
+        import decord                                     # the reference's decoder (video_processor.py:204-205)
+        vr = decord.VideoReader(uri=video_path, height=224, width=224)
+        idx = pick(len(vr))
+        return vr.get_batch(idx).asnumpy()
+    except ImportError:
+        pass
+    import cv2
+    cap = cv2.VideoCapture(video_path)
+    if not cap.isOpened():
+        raise IOError(f"cannot open {video_path}")
+    frames = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        frames.append(fr)
+    cap.release()
+    if not frames:
+        raise IOError(f"no frames decoded from {video_path}")
+    idx = pick(len(frames))
+    return np.stack([cv2.resize(cv2.cvtColor(frames[i], cv2.COLOR_BGR2RGB), (224, 224)) for i in idx])
+
+
+def read_wav(audio_path: str, sample_rate: int = 16000) -> torch.Tensor:
+    """-> float32 [channels, n] at ``sample_rate`` (torchaudio.load semantics: int PCM scaled to [-1, 1))."""
+    from scipy.io import wavfile
+    sr, data = wavfile.read(audio_path)
+    if data.dtype == np.int16:
+        wav = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        wav = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        wav = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        wav = data.astype(np.float32)
+    wav = torch.from_numpy(np.ascontiguousarray(wav.T if wav.ndim == 2 else wav[None]))
+    if sr != sample_rate:                                  # data.py:186-187
+        import torchaudio
+        wav = torchaudio.functional.resample(wav, orig_freq=sr, new_freq=sample_rate)
+    return wav
+
+
+# --------------------------------------------------------------------------------------------- extractor
+class MultimodalFeatureExtractor:
+    """Same method surface as the reference's extractor class (extract_*_features -> np.ndarray or None)."""
+
+    def __init__(self, visual_encoder=None, acoustic_encoder=None, fusion=None, device: str = "cuda:0",
+                 mer_factory_output: Optional[str] = None):
+        self.device = torch.device(device)
+        self.encoders = {"visual": visual_encoder, "acoustic": acoustic_encoder}
+        self.multi_fusion_model = fusion
+        self.mer_factory_output = mer_factory_output
+
+    # ---- single-sample calls, reference signatures
+    def extract_frame_features(self, video_path, n_frms=8, sampling="uniform", video_name=None):
+        try:
+            frames = read_video_frames(video_path, lambda vlen: frame_indices(vlen, n_frms, sampling, video_name,
+                                                                              self.mer_factory_output))
+            u8 = torch.from_numpy(frames).to(self.device).permute(0, 3, 1, 2).contiguous()       # [T,3,224,224] u8
+            return self._visual(u8[None])[0]
+        except Exception as e:                                                                  # :227-229
+            print(f"Error extracting frame features from {video_path}: {e}")
+            return None
+
+    def extract_face_features(self, face_npy_path, n_frms=8):
+        try:
+            faces = np.load(face_npy_path)
+            idx = sampling.uniform_frame_indices(len(faces), n_frms)
+            u8 = staging.stage_faces(faces, idx, self.device)                                    # [T,3,224,224] u8
+            return self._visual(u8[None])[0]
+        except Exception as e:                                                                  # :587-589
+            print(f"Error extracting face features from {face_npy_path}: {e}")
+            return None
+
+    def extract_audio_features(self, audio_path, clips_per_video=8):
+        try:
+            raw = staging.stage_audio(read_wav(audio_path), clips_per_video=clips_per_video, device=self.device)
+            with torch.no_grad():
+                feats = self.encoders["acoustic"](None, raw[None])                               # [1,T,1024]
+            return feats[0].float().cpu().numpy()
+        except Exception:                                                                        # :610-612 (silent)
+            return None
+
+    def extract_multi_features(self, face_features, audio_features):
+        try:
+            if self.multi_fusion_model is None:
+                raise RuntimeError("Multi fusion model not loaded.")
+            f = torch.from_numpy(np.asarray(face_features)).float()[None].to(self.device)
+            a = torch.from_numpy(np.asarray(audio_features)).float()[None].to(self.device)
+            multi_hidden, _ = self.multi_fusion_model.encode_multi_merge(f, a)
+            return multi_hidden[0].float().cpu().numpy()
+        except Exception as e:
+            print(f"Error extracting multi features: {e}")
+            return None
+
+    # ---- helpers
+    def _visual(self, u8_btchw: torch.Tensor) -> np.ndarray:
+        """[b,T,3,224,224] uint8 -> [b,T,768] fp32 numpy.  The encoder wrapper takes the reference's float layout
+        [b,3,t,224,224]; the engine behind it also accepts uint8 frames directly, which skips the float round trip."""
+        enc = self.encoders["visual"]
+        b, t = u8_btchw.shape[:2]
+        with torch.no_grad():
+            if hasattr(enc, "_ensure_engine"):
+                eng = enc._ensure_engine(u8_btchw.device)
+                feats = eng.clip_forward(u8_btchw.reshape(b * t, 3, 224, 224)).reshape(b, t, -1)
+            else:
+                feats = enc(None, u8_btchw.permute(0, 2, 1, 3, 4).float())
+        return feats.float().cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------- the sweep
+def save_dirs(args) -> Dict[str, str]:
+    """Directory names of extract_multimodal_features_precompute.py:823-849."""
+    root = os.path.join(args.save_root, args.dataset)
+    d: Dict[str, str] = {}
+    if args.modality in ("frame", "all"):
+        d["frame"] = os.path.join(root, f"frame_{args.visual_encoder}_{args.frame_sampling}_{args.frame_n_frms}frms")
+    if args.modality in ("face", "all"):
+        d["face"] = os.path.join(root, f"face_{args.visual_encoder}_8frms")
+    if args.modality in ("audio", "all", "multi"):
+        d["audio"] = os.path.join(root, f"audio_{args.acoustic_encoder}_{args.clips_per_video}clips")
+    if args.modality in ("multi", "all") and not args.skip_multi_preextract:
+        d["multi"] = os.path.join(root, f"multi_{args.visual_encoder}_{args.acoustic_encoder}_complete")
+    for p in d.values():
+        os.makedirs(p, exist_ok=True)
+    return d
+
+
+def run_sweep(args, extractor, sample_names: List[str], log=print) -> Dict[str, int]:
+    """The per-sample loop of the reference (:892-1024) over this rank's samples."""
+    dirs = save_dirs(args)
+    stats = {k: 0 for k in ("frame_success", "face_success", "audio_success", "audio_failed", "multi_success", "multi_failed",
+                            "skipped_existing")}
+    quiet = args.quiet
+    for name in sample_names:
+        if "frame" in dirs:
+            out = os.path.join(dirs["frame"], f"{name}.npy")
+            if os.path.exists(out):
+                stats["skipped_existing"] += 1
+            else:
+                video = os.path.join(args.video_root, f"{name}.mp4")
+                if os.path.exists(video) or os.path.exists(os.path.splitext(video)[0] + ".npy"):
+                    f = extractor.extract_frame_features(video_path=video, n_frms=args.frame_n_frms,
+                                                         sampling=args.frame_sampling, video_name=name)
+                    if f is not None:
+                        np.save(out, f)
+                        stats["frame_success"] += 1
+                        if not quiet:
+                            log(f"Frame: {name} -> {f.shape}")
+        if "face" in dirs:
+            out = os.path.join(dirs["face"], f"{name}.npy")
+            if os.path.exists(out):
+                stats["skipped_existing"] += 1
+            else:
+                face_npy = os.path.join(args.face_root, name, f"{name}.npy")
+                if os.path.exists(face_npy):
+                    f = extractor.extract_face_features(face_npy, n_frms=8)
+                    if f is not None:
+                        np.save(out, f)
+                        stats["face_success"] += 1
+                        if not quiet:
+                            log(f"Face: {name} -> {f.shape}")
+                elif not quiet:
+                    log(f"Face: {name} -> file not found: {face_npy}")
+        if args.modality in ("audio", "all"):
+            out = os.path.join(dirs["audio"], f"{name}.npy")
+            if os.path.exists(out):
+                stats["skipped_existing"] += 1
+            else:
+                wav = os.path.join(args.audio_root, f"{name}.wav")
+                f = extractor.extract_audio_features(wav, clips_per_video=args.clips_per_video) if os.path.exists(wav) else None
+                if f is not None:
+                    np.save(out, f)
+                    stats["audio_success"] += 1
+                    if not quiet:
+                        log(f"Audio: {name} -> {f.shape}")
+                else:                                          # missing file or failed processing: zero-filled (:965-975)
+                    np.save(out, np.zeros((args.clips_per_video, 1024), dtype=np.float32))
+                    stats["audio_failed"] += 1
+                    if not quiet:
+                        log(f"Audio: {name} -> zero-padded")
+        if "multi" in dirs:
+            out = os.path.join(dirs["multi"], f"{name}.npy")
+            if os.path.exists(out):
+                stats["skipped_existing"] += 1
+            else:
+                face_npy = os.path.join(args.face_root, name, f"{name}.npy")
+                wav = os.path.join(args.audio_root, f"{name}.wav")
+                ff = extractor.extract_face_features(face_npy, n_frms=8) if os.path.exists(face_npy) else None
+                af = extractor.extract_audio_features(wav, clips_per_video=args.clips_per_video) if os.path.exists(wav) else None
+                m = extractor.extract_multi_features(ff, af) if (ff is not None and af is not None) else None
+                if m is not None:
+                    np.save(out, m)
+                    stats["multi_success"] += 1
+                    if not quiet:
+                        log(f"Multi: {name} -> {m.shape}")
+                else:
+                    stats["multi_failed"] += 1
+    return stats
+
+
+def read_sample_names(args) -> List[str]:
+    """--sample_list (one name per line) or --csv_path / --csv_column (:1120-1123 and the csv branch)."""
+    if bool(args.sample_list) == bool(args.csv_path):
+        raise ValueError("Either --sample_list or --csv_path must be provided" if not args.sample_list
+                         else "Cannot specify both --sample_list and --csv_path, choose one")
+    if args.sample_list:
+        with open(args.sample_list, "r") as f:
+            return [ln.strip() for ln in f if ln.strip()]
+    import pandas as pd
+    df = pd.read_csv(args.csv_path)
+    return [str(x) for x in df[args.csv_column].tolist()]
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="AffectGPT multimodal feature extraction (B200-native path)")
+    p.add_argument("--dataset", type=str, required=True, choices=DATASETS)
+    p.add_argument("--modality", type=str, default="all", choices=["frame", "face", "audio", "multi", "all"])
+    p.add_argument("--device", type=str, default="cuda:0")
+    p.add_argument("--quiet", action="store_true")
+    p.add_argument("--skip-multi-preextract", action="store_true", dest="skip_multi_preextract")
+    p.add_argument("--video_root", type=str)
+    p.add_argument("--face_root", type=str)
+    p.add_argument("--audio_root", type=str)
+    p.add_argument("--sample_list", type=str)
+    p.add_argument("--csv_path", type=str)
+    p.add_argument("--csv_column", type=str, default="names")
+    p.add_argument("--save_root", type=str, default="./preextracted_features")
+    p.add_argument("--mer-factory-output", type=str, dest="mer_factory_output")
+    p.add_argument("--visual_encoder", type=str, default="CLIP_VIT_LARGE", choices=["CLIP_VIT_LARGE"])
+    p.add_argument("--acoustic_encoder", type=str, default="HUBERT_LARGE", choices=["HUBERT_LARGE"])
+    p.add_argument("--frame_n_frms", type=int, default=8)
+    p.add_argument("--frame_sampling", type=str, default="uniform", choices=["uniform", "headtail", "emotion_peak"])
+    p.add_argument("--clips_per_video", type=int, default=8)
+    p.add_argument("--n_frms", type=int, default=8, help="Deprecated: use --frame_n_frms instead")
+    p.add_argument("--fusion_ckpt", type=str, help="AffectGPT checkpoint (ckpt['model']) for the multi features")
+    return p
+
+
+def validate_args(args) -> None:
+    """The argument checks of the reference's main() (:1098-1123)."""
+    if args.frame_n_frms == 8 and args.n_frms != 8:
+        args.frame_n_frms = args.n_frms
+    if args.modality in ("frame", "all") and not args.video_root:
+        raise ValueError("video_root is required when extracting frame features")
+    if args.modality in ("face", "all", "multi") and not args.face_root:
+        raise ValueError("face_root is required when extracting face or multi features")
+    if args.modality in ("audio", "all", "multi") and not args.audio_root:
+        raise ValueError("audio_root is required when extracting audio or multi features")
+    if args.frame_sampling == "emotion_peak" and args.modality in ("frame", "all") and not args.mer_factory_output:
+        raise ValueError("mer_factory_output is required when using emotion_peak sampling")
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    args = build_parser().parse_args(argv)
+    validate_args(args)
+    names = read_sample_names(args)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:                                            # one replica per GPU, samples rank::world
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        args.device = f"cuda:{local}"
+        names = [names[i] for i in shard_indices(len(names), rank, world)]
+    from .fusion import AffectGPTFusion
+    from .registry import registry
+    visual = registry.get_visual_encoder_class(args.visual_encoder)()
+    acoustic = registry.get_acoustic_encoder_class(args.acoustic_encoder)()
+    fusion = None
+    if args.modality in ("multi", "all") and not args.skip_multi_preextract:
+        if not args.fusion_ckpt:
+            raise ValueError("--fusion_ckpt is required to pre-extract multi features (or pass --skip-multi-preextract)")
+        ckpt = torch.load(args.fusion_ckpt, map_location="cpu")
+        fusion = AffectGPTFusion(visual, acoustic)
+        fusion.load_state_dict(ckpt.get("model", ckpt))
+    extractor = MultimodalFeatureExtractor(visual, acoustic, fusion, device=args.device,
+                                           mer_factory_output=args.mer_factory_output)
+    stats = run_sweep(args, extractor, names)
+    print(f"[rank {rank}/{world}] " + ", ".join(f"{k}={v}" for k, v in stats.items()))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,119 @@
+"""Sweep CLI host logic (no GPU): directory layout, resume, zero-fill and argument rules of the reference's
+extract_multimodal_features_precompute.py (:823-849, 892-1024, 1098-1123), with a stub extractor."""
+import os
+
+import numpy as np
+import pytest
+
+from affectgpt_b200 import extract as X
+
+
+class StubExtractor:
+    def __init__(self):
+        self.calls = []
+
+    def extract_frame_features(self, video_path, n_frms=8, sampling="uniform", video_name=None):
+        self.calls.append(("frame", video_name, n_frms, sampling))
+        return np.full((n_frms, 768), 1.0, np.float32)
+
+    def extract_face_features(self, face_npy_path, n_frms=8):
+        self.calls.append(("face", os.path.basename(face_npy_path), n_frms))
+        return np.full((n_frms, 768), 2.0, np.float32)
+
+    def extract_audio_features(self, audio_path, clips_per_video=8):
+        self.calls.append(("audio", os.path.basename(audio_path)))
+        return None if "broken" in audio_path else np.full((clips_per_video, 1024), 3.0, np.float32)
+
+    def extract_multi_features(self, face_features, audio_features):
+        return np.full((1024,), 4.0, np.float32)
+
+
+def _dataset(tmp_path, names):
+    v, f, a = tmp_path / "video", tmp_path / "face", tmp_path / "audio"
+    for d in (v, f, a):
+        d.mkdir()
+    for n in names:
+        (v / f"{n}.mp4").write_bytes(b"x")
+        (f / n).mkdir()
+        np.save(f / n / f"{n}.npy", np.zeros((3, 4, 4, 3), np.uint8))
+        if n != "noaudio":
+            (a / f"{n}.wav").write_bytes(b"x")
+    lst = tmp_path / "names.txt"
+    lst.write_text("\n".join(names) + "\n")
+    return ["--dataset", "mer2023", "--video_root", str(v), "--face_root", str(f), "--audio_root", str(a),
+            "--sample_list", str(lst), "--save_root", str(tmp_path / "out"), "--quiet"]
+
+
+def test_layout_zero_fill_and_resume(tmp_path):
+    argv = _dataset(tmp_path, ["s1", "broken", "noaudio"]) + ["--frame_sampling", "emotion_peak", "--frame_n_frms", "1",
+                                                                "--mer-factory-output", str(tmp_path)]
+    args = X.build_parser().parse_args(argv)
+    X.validate_args(args)
+    names = X.read_sample_names(args)
+    assert names == ["s1", "broken", "noaudio"]
+    ex = StubExtractor()
+    stats = X.run_sweep(args, ex, names, log=lambda *_: None)
+    root = tmp_path / "out" / "mer2023"
+    assert sorted(os.listdir(root)) == ["audio_HUBERT_LARGE_8clips", "face_CLIP_VIT_LARGE_8frms",
+                                        "frame_CLIP_VIT_LARGE_emotion_peak_1frms", "multi_CLIP_VIT_LARGE_HUBERT_LARGE_complete"]
+    assert np.load(root / "frame_CLIP_VIT_LARGE_emotion_peak_1frms" / "s1.npy").shape == (1, 768)
+    assert np.load(root / "face_CLIP_VIT_LARGE_8frms" / "s1.npy").shape == (8, 768)
+    for n in ("broken", "noaudio"):                          # failed processing / missing wav: zero-filled [clips, 1024]
+        z = np.load(root / "audio_HUBERT_LARGE_8clips" / f"{n}.npy")
+        assert z.shape == (8, 1024) and z.dtype == np.float32 and not z.any()
+    assert np.load(root / "audio_HUBERT_LARGE_8clips" / "s1.npy").mean() == 3.0
+    assert np.load(root / "multi_CLIP_VIT_LARGE_HUBERT_LARGE_complete" / "s1.npy").shape == (1024,)
+    assert not (root / "multi_CLIP_VIT_LARGE_HUBERT_LARGE_complete" / "broken.npy").exists()
+    assert stats["audio_success"] == 1 and stats["audio_failed"] == 2 and stats["multi_success"] == 1
+    assert ("frame", "s1", 1, "emotion_peak") in ex.calls
+    ex2 = StubExtractor()                                    # second run: everything that exists is skipped
+    stats2 = X.run_sweep(args, ex2, names, log=lambda *_: None)
+    assert stats2["frame_success"] == stats2["face_success"] == stats2["audio_success"] == 0
+    assert [c for c in ex2.calls if c[0] == "frame"] == []
+
+
+def test_skip_multi_and_modality_subsets(tmp_path):
+    argv = _dataset(tmp_path, ["a"]) + ["--modality", "audio", "--clips_per_video", "4"]
+    args = X.build_parser().parse_args(argv)
+    X.validate_args(args)
+    X.run_sweep(args, StubExtractor(), ["a"], log=lambda *_: None)
+    root = tmp_path / "out" / "mer2023"
+    assert os.listdir(root) == ["audio_HUBERT_LARGE_4clips"]
+    args2 = X.build_parser().parse_args(_dataset_args_only(argv) + ["--skip-multi-preextract"])
+    assert "multi" not in X.save_dirs(args2)
+
+
+def _dataset_args_only(argv):
+    out = list(argv)
+    i = out.index("--modality")
+    del out[i:i + 2]
+    return out
+
+
+def test_argument_rules_match_reference():
+    p = X.build_parser()
+    with pytest.raises(ValueError, match="video_root"):
+        X.validate_args(p.parse_args(["--dataset", "meld", "--modality", "frame", "--sample_list", "x"]))
+    with pytest.raises(ValueError, match="face_root"):
+        X.validate_args(p.parse_args(["--dataset", "meld", "--modality", "multi", "--audio_root", "a", "--sample_list", "x"]))
+    with pytest.raises(ValueError, match="audio_root"):
+        X.validate_args(p.parse_args(["--dataset", "meld", "--modality", "audio", "--sample_list", "x"]))
+    with pytest.raises(ValueError, match="Either"):
+        X.read_sample_names(p.parse_args(["--dataset", "meld", "--modality", "audio", "--audio_root", "a"]))
+    with pytest.raises(ValueError, match="both"):
+        X.read_sample_names(p.parse_args(["--dataset", "meld", "--sample_list", "x", "--csv_path", "y"]))
+    a = p.parse_args(["--dataset", "meld", "--modality", "audio", "--audio_root", "a", "--sample_list", "x", "--n_frms", "4"])
+    X.validate_args(a)
+    assert a.frame_n_frms == 4                               # deprecated --n_frms still honoured (:1091-1095)
+    with pytest.raises(SystemExit):
+        p.parse_args(["--dataset", "not-a-dataset"])
+
+
+def test_csv_sample_source_and_frame_index_rules(tmp_path):
+    csv = tmp_path / "s.csv"
+    csv.write_text("names,label\nclip_a,1\nclip_b,0\n")
+    args = X.build_parser().parse_args(["--dataset", "meld", "--csv_path", str(csv)])
+    assert X.read_sample_names(args) == ["clip_a", "clip_b"]
+    assert X.frame_indices(88, 8, "uniform") == [0, 11, 22, 33, 44, 55, 66, 77]
+    assert X.frame_indices(88, 8, "emotion_peak") == [44] * 8
+    assert X.frame_indices(5, 8, "uniform") == [0, 1, 2, 3, 4, 4, 4, 4]

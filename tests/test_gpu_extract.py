@@ -1,0 +1,80 @@
+"""End-to-end pre-extraction sweep on the GPU (small random-init encoders) against the oracle run sample by sample
+the way the reference extractor does (b = 1 per call): same files, same shapes, features inside the bf16 gate."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_path as R
+from oracle import sampling as OS
+from tests.gpu_util import gate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _write_dataset(root, names):
+    from scipy.io import wavfile
+    rng = np.random.default_rng(11)
+    v, f, a = root / "video", root / "face", root / "audio"
+    for d in (v, f, a):
+        d.mkdir()
+    data = {}
+    for i, n in enumerate(names):
+        frames = rng.integers(0, 256, size=(20 + 3 * i, 224, 224, 3), dtype=np.uint8)      # pre-decoded RGB stack
+        np.save(v / f"{n}.npy", frames)
+        faces = rng.integers(0, 256, size=(11 + i, 96, 80, 3), dtype=np.uint8)
+        (f / n).mkdir()
+        np.save(f / n / f"{n}.npy", faces)
+        nsamp = [55357, 30000, 96000][i % 3]
+        pcm = (rng.standard_normal((nsamp, 2 if i == 1 else 1)) * 3000 * (1 + i)).astype(np.int16)
+        wavfile.write(a / f"{n}.wav", 16000, pcm if i == 1 else pcm[:, 0])
+        data[n] = (frames, faces, pcm)
+    (root / "names.txt").write_text("\n".join(names + ["missing_everything"]) + "\n")
+    return data
+
+
+def test_sweep_matches_oracle_per_sample(tmp_path):
+    import cv2
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import extract as X
+    names = ["clipA", "clipB", "clipC"]
+    data = _write_dataset(tmp_path, names)
+    clip = R.build_clip_vision(num_layers=2, seed=1234)
+    hub = R.build_hubert(num_layers=3, feat_extract_norm="layer", seed=1234)
+    fus = R.build_fusion_state(seed=1234)
+    model = agb.build_path(clip.state_dict(), hub.state_dict(), fus, device=DEV, vit_layers=2, hubert_layers=3)
+    ex = X.MultimodalFeatureExtractor(model.visual_encoder, model.acoustic_encoder, model, device=DEV)
+    args = X.build_parser().parse_args([
+        "--dataset", "mer2024", "--video_root", str(tmp_path / "video"), "--face_root", str(tmp_path / "face"),
+        "--audio_root", str(tmp_path / "audio"), "--sample_list", str(tmp_path / "names.txt"),
+        "--save_root", str(tmp_path / "out"), "--quiet"])
+    X.validate_args(args)
+    stats = X.run_sweep(args, ex, X.read_sample_names(args), log=lambda *_: None)
+    assert stats["frame_success"] == 3 and stats["face_success"] == 3 and stats["audio_success"] == 3
+    assert stats["audio_failed"] == 1 and stats["multi_success"] == 3
+    root = tmp_path / "out" / "mer2024"
+    z = np.load(root / "audio_HUBERT_LARGE_8clips" / "missing_everything.npy")
+    assert z.shape == (8, 1024) and not z.any()
+    for n in names:
+        frames, faces, pcm = data[n]
+        # oracle, the way the reference extractor runs it: one sample per call
+        idx = OS.uniform_indices(len(frames), 8)
+        raw = torch.from_numpy(frames[idx]).permute(3, 0, 1, 2).float()[None]                 # [1,3,8,224,224]
+        want_frame = R.clip_vit_large_forward(clip, raw)[0]
+        fidx = OS.uniform_indices(len(faces), 8)
+        rf = np.stack([cv2.resize(fc, (224, 224)) for fc in faces])[fidx]                     # load_face order: resize, sample
+        want_face = R.clip_vit_large_forward(clip, torch.from_numpy(rf).permute(3, 0, 1, 2).float()[None])[0]
+        wav = torch.from_numpy(pcm.astype(np.float32) / 32768.0).T.contiguous()               # [ch, n]
+        segs, _ = OS.audio_segments(wav)
+        want_audio = R.hubert_large_forward(hub, segs[None])[0]
+        want_multi = R.encode_multi_attention(fus, want_face[None], want_audio[None])[0][0]
+        for sub, want in (("frame_CLIP_VIT_LARGE_uniform_8frms", want_frame), ("face_CLIP_VIT_LARGE_8frms", want_face),
+                          ("audio_HUBERT_LARGE_8clips", want_audio)):
+            got = np.load(root / sub / f"{n}.npy")
+            assert got.dtype == np.float32 and got.shape == tuple(want.shape)
+            gate(torch.from_numpy(got), want, f"{sub}/{n}")
+        gm = np.load(root / "multi_CLIP_VIT_LARGE_HUBERT_LARGE_complete" / f"{n}.npy")
+        assert gm.shape == (1024,)
+        gate(torch.from_numpy(gm)[None], want_multi[None], f"multi/{n}")
