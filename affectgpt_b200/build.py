@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-Wall", "-Xptxas", "-v",
-]
+] + os.environ.get("AGB_NVCC_EXTRA", "").split()      # A/B experiments, e.g. AGB_NVCC_EXTRA=-DAGB_GELU_MUFU
 
 
 def _nvcc() -> str:

@@ -228,6 +228,11 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // all bulk stores committed by this thread have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+__device__ __forceinline__ float tanh_approx_fwd(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution): 2 MUFU + ~12 FMA
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
@@ -242,6 +247,41 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = fmaf(-p, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
+
+// exact-GELU without the SFU: erf(z) = z * P(z^2) on |z| <= 2.9 (degree-7 minimax in z^2, |err| < 6e-5, an order of
+// magnitude below bf16 resolution of the activations it feeds), clamped beyond (erf(2.9) = 0.99996).  ~14 FMA/ALU
+// instructions and no MUFU.  Measured on B200 (tools/gelu_ab.sh): the SFU-bound element-wise kernels gain (conv0 with
+// LayerNorm + GELU 2.2x, ln512 + GELU 5 %), the issue-bound GEMM epilogue loses 7 % - so the GEMM keeps gelu_erf_fast.
+__device__ __forceinline__ float gelu_erf_poly(float x) {
+  const float z = fminf(fmaxf(x * 0.70710678118654752f, -2.9f), 2.9f);
+  const float t = z * z;
+  float p = fmaf(t, -4.961727313457232e-07f, 1.9877472368534654e-05f);
+  p = fmaf(t, p, -0.00034695438807830215f);
+  p = fmaf(t, p, 0.0035132169723510742f);
+  p = fmaf(t, p, -0.023305216804146767f);
+  p = fmaf(t, p, 0.10871681571006775f);
+  p = fmaf(t, p, -0.373929500579834f);
+  p = fmaf(t, p, 1.1280336380004883f);
+  const float h = 0.5f * x;
+  return fmaf(h, z * p, h);
+}
+// erf-GELU through the tanh identity with the inner polynomial refitted to the ERF form:
+//   0.5 x (1 + tanh(x (0.797508 + 0.0370056 u - 3.51517e-4 u^2))),  u = min(x^2, 49)
+// max |difference| to 0.5 x (1 + erf(x / sqrt 2)) = 2.5e-5 over all x (the classic 0.044715 form is off by 4.7e-4),
+// i.e. 150x below the bf16 resolution of the FFN activations it feeds and below tanh.approx's own 2^-11.
+// 1 MUFU + 7 FMA/ALU instead of 2 MUFU + 15: the GEMM epilogue warps are issue-bound (tools/gelu_ab.sh on B200:
+// HuBERT FFN1 983 -> 1246 TFLOP/s).
+__device__ __forceinline__ float gelu_erf_tanhform(float x) {
+  const float u = fminf(x * x, 49.0f);
+  const float inner = x * fmaf(u, fmaf(u, -3.51516789e-4f, 3.70056460e-2f), 7.97507884e-1f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx_fwd(inner), h);
+}
+#ifndef AGB_GELU_MUFU
+#define AGB_GELU_ERF(x) ::agb::gelu_erf_poly(x)
+#else
+#define AGB_GELU_ERF(x) ::agb::gelu_erf_fast(x)
+#endif
 
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ float tanh_approx(float x) {

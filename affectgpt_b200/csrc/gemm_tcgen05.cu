@@ -33,6 +33,12 @@
 #include "agb_internal.h"
 #include "agb_ptx.cuh"
 
+#ifdef AGB_GEMM_GELU_EXACT
+#define AGB_GEMM_GELU(x) gelu_erf_fast(x)       // A&S 7.1.26: 2 MUFU + 15 FMA, |err| < 1.5e-7
+#else
+#define AGB_GEMM_GELU(x) gelu_erf_tanhform(x)   // 1 MUFU + 7 FMA, |formula err| < 2.5e-5
+#endif
+
 namespace agb {
 
 namespace {
@@ -260,7 +266,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 32; ++j) x[j] = quick_gelu(x[j]);
         } else if constexpr (ACT == ACT_GELU_ERF) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = gelu_erf_fast(x[j]);
+          for (int j = 0; j < 32; ++j) x[j] = AGB_GEMM_GELU(x[j]);
         }
         if (p.has_f32) {
           // ---- fp32 tile [32 rows x 32 cols] -> staging -> TMA store / reduce-add

@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(256) conv0_kernel(const float* __restrict__ wa
       for (int i = 0; i < 16; ++i) { const float d = acc[r][i] - m; ss += d * d; }
       const float rs = rsqrtf(warp_sum(ss) * (1.0f / 512.f) + 1e-5f);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) y[i] = gelu_erf_fast((acc[r][i] - m) * rs * gg[i] + bb[i]);
+      for (int i = 0; i < 16; ++i) y[i] = AGB_GELU_ERF((acc[r][i] - m) * rs * gg[i] + bb[i]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) y[i] = gelu_erf_fast((acc[r][i] - cm[i]) * cr[i] * gg[i] + bb[i]);
+      for (int i = 0; i < 16; ++i) y[i] = AGB_GELU_ERF((acc[r][i] - cm[i]) * cr[i] * gg[i] + bb[i]);
     }
     bf16* orow = out + (seg * kL0Pad + t) * 512;
     uint4 o0, o1;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) gelu_bf16_kernel(bf16* x, long long n8) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float2 f = __bfloat1622float2(h[k]);
-      h[k] = __floats2bfloat162_rn(gelu_erf_fast(f.x), gelu_erf_fast(f.y));
+      h[k] = __floats2bfloat162_rn(AGB_GELU_ERF(f.x), AGB_GELU_ERF(f.y));
     }
     reinterpret_cast<uint4*>(x)[i] = u;
   }

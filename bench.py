@@ -46,6 +46,17 @@ def read_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def gemm_traffic_per_launch():
+    """Mean DRAM bytes (read + write) per GEMM launch of one C2 step, from the committed ncu launch list
+    (profiles/r01_traffic.json, produced by tools/summarize_launches.py from an ncu capture of this very command);
+    None when no capture has been committed."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return float(json.load(open(p))["gemm_kernel"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -109,21 +120,33 @@ def cpu_oracle_clips_per_sec(n_clips: int, warmup: int = 1):
     return n_clips / dt, cores, dt
 
 
+def workload_config(clips_per_gpu: int, world: int) -> dict:
+    """`config` of the JSON line; shared by both arms (the reference arm measures the same workload on the host)."""
+    tf_per_clip = (8 * GF_VIT_FRAME + 8 * GF_HUBERT_SEG + GF_FUSE_CLIP) / 1e3
+    return {"workload": f"C2: {clips_per_gpu} clips/GPU x (8 frames 224^2 + 8x2s 16kHz audio) -> frame/audio/multi tokens @3584",
+            "clips_per_gpu": clips_per_gpu, "weights": "random-init CLIP ViT-L/14 + HuBERT-large (layer-norm conv) + heads",
+            "cache": "inputs (373 MB/step) and activations exceed the 126 MB L2", "parallelism": f"dp{world}",
+            "tflop_per_clip": tf_per_clip}
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle port: HF fp32 modules + the restated wrappers, one clip
+    per call as the reference's extractor runs it), all host threads, on rank 0 only.  Each "step" is a bounded sample
+    of the C2 workload: ONE clip of the 64 (the per-clip cost is batch-independent on the CPU), so that
+    `--steps K --warmup W` stays within minutes; value = clips / second over the K timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     per_step = 1
-    vals = []
-    from oracle import reference_path as R  # noqa: F401  (the CPU arm IS the oracle; nothing of ours on this path)
-    cps, cores, _ = cpu_oracle_clips_per_sec(per_step * max(args.steps, 1), warmup=min(args.warmup, 1))
-    vals.append(cps)
-    line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / cps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 clip shape (8 frames 224^2 + 8x2s audio), CPU reference path, batch 1 per call"},
+    cps, cores, dt = cpu_oracle_clips_per_sec(per_step * max(args.steps, 1), warmup=max(min(args.warmup, 2), 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": max(args.gpus, world),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_step / cps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.clips, max(args.gpus, world)),
             "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step * max(args.steps, 1)} clips at batch 1 after {min(args.warmup, 1)} warm-up"},
+                             "sample": f"{per_step} clip of the batch per step, {max(args.steps, 1)} timed steps at batch 1 "
+                                       f"(oracle: HF fp32 + restated wrappers), {dt:.1f} s"},
             "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -231,18 +254,19 @@ def main():
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"C2: {B} clips/GPU x (8 frames 224^2 + 8x2s 16kHz audio) -> frame/audio/multi tokens @3584",
-                   "clips_per_gpu": B, "weights": "random-init CLIP ViT-L/14 + HuBERT-large (layer-norm conv) + heads",
-                   "cache": "inputs (373 MB/step) and activations exceed the 126 MB L2", "parallelism": f"dp{world}",
-                   "tflop_per_clip": tf_per_clip},
+        "config": workload_config(B, world),
         "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h_frames.numel() * 4 + h_audio.numel() * 4), "d2h_bytes_per_step": int(h_tokens.numel() * 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": None, "kernel": "gemm_kernel (tcgen05, all GEMM launches)",
+                     "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": gemm_traffic_per_launch(),
+                     "traffic_unit": "bytes per launch (dram read+write, mean over the GEMM launches of one step; ncu, profiles/)",
+                     "flops_per_launch": g["flops"] / max(g["launches"], 1), "ms_per_launch": g["ms"] / max(g["launches"], 1),
+                     "kernel": "gemm_kernel (tcgen05, all GEMM launches)",
                      "peak_source": peaks["source"] + ", sustained", "gemm_launches": g["launches"], "gemm_ms_per_step": g["ms"] / args.steps,
                      "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peaks["bf16_sustained"],
                      "time_share": {k: v["ms"] / tot_ms for k, v in prof.items()},
+                     "category_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
                      "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12) if prof["attention"]["ms"] > 0 else 0.0,
                      "layernorm_gbs": (prof["layernorm"]["bytes"] / (prof["layernorm"]["ms"] / 1e3) / 1e9) if prof["layernorm"]["ms"] > 0 else 0.0,
                      "frontend_gbs": (prof["frontend"]["bytes"] / (prof["frontend"]["ms"] / 1e3) / 1e9) if prof["frontend"]["ms"] > 0 else 0.0},
