@@ -16,7 +16,7 @@ CSRC = HERE / "csrc"
 LIB = HERE / "libagb.so"
 STAMP = HERE / "csrc" / ".build_stamp"
 
-SOURCES = ["agb_api.cu", "gemm_tcgen05.cu", "layernorm.cu", "attention.cu", "attention_tc2.cu", "vit.cu", "hubert.cu",
+SOURCES = ["agb_api.cu", "gemm_tcgen05.cu", "layernorm.cu", "attention.cu", "attention_tc2.cu", "vit.cu", "hubert.cu", "conv0_tc.cu",
            "fusion.cu", "qformer.cu", "staging.cu", "splice.cu", "pack.cu", "profile.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -391,8 +391,8 @@ int ensure_hub_ws(agb_ctx* c, int64_t segs) {
   if (int r = dev_alloc(c, &c->h_qkv, M * 3072)) return r;
   if (int r = dev_alloc(c, &c->h_attn, M * 1024)) return r;
   if (int r = dev_alloc(c, &c->h_h1, M * 4096)) return r;
-  if (c->cfg.hubert_conv_norm == 1)
-    if (int r = dev_alloc(c, &c->h_gn_acc, (size_t)segs * 1024)) return r;
+  // group variant: per-(segment, channel) fp64 sum / sumsq; layer variant: the 32 KB packed conv0 filter matrix
+  if (int r = dev_alloc(c, &c->h_gn_acc, c->cfg.hubert_conv_norm == 1 ? (size_t)segs * 1024 : (size_t)4096)) return r;
   c->h_cap = segs;
   return 0;
 }
@@ -884,7 +884,7 @@ int agb_op_conv0(const float* wav, int64_t nseg, int64_t seg_per_norm_group, int
   double* gn = nullptr;
   AGB_CHECK_CUDA(cudaMalloc(&stats, sizeof(float) * 2 * groups));
   AGB_CHECK_CUDA(cudaMalloc(&acc, sizeof(double) * 2 * groups));
-  if (norm_mode == 1) AGB_CHECK_CUDA(cudaMalloc(&gn, sizeof(double) * 1024 * nseg));
+  AGB_CHECK_CUDA(cudaMalloc(&gn, norm_mode == 1 ? sizeof(double) * 1024 * nseg : sizeof(double) * 4096));
   int r = wave_stats(wav, nseg, 32000, spg, stats, do_normalize, acc, s);
   if (!r) r = hubert_conv0(wav, stats, spg, 0, nseg, w, bias, gamma, beta, norm_mode, reinterpret_cast<float*>(gn),
                            static_cast<bf16*>(out), s);

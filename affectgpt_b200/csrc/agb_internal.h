@@ -114,6 +114,10 @@ int wave_stats(const float* wav, int64_t nseg, int64_t samples, int64_t seg_per_
 int hubert_conv0(const float* wav, const float* stats, int64_t seg_per_group, int64_t seg_offset, int64_t nseg, const float* w /*[512,10]*/,
                  const float* bias, const float* g, const float* b, int norm_mode /*0 layer,1 group*/,
                  float* gn_scratch /*nseg*1024 doubles, group mode only*/, bf16* out /*[nseg*6400,512]*/, cudaStream_t s);
+// conv0_tc.cu: the "layer" variant on tcgen05 (im2col tile x filter matrix in TMEM, LayerNorm + GELU epilogue)
+int hubert_conv0_layer_tc(const float* wav, const float* stats, int64_t seg_per_group, int64_t seg_offset, int64_t nseg,
+                          const float* w, const float* bias, const float* g, const float* b, bf16* wp_scratch /*[512*32]*/,
+                          bf16* out, cudaStream_t s);
 int gelu_bf16_inplace(bf16* x, int64_t n, cudaStream_t s);
 // pooled[seq, :] (+)= scale * mean_{t<valid} f(x[seq, t, :]); f = identity or LayerNorm(gamma,beta)
 int seq_mean_pool(const float* x, int nseq, int seq_stride, int seq_valid, const float* gamma, const float* beta,
