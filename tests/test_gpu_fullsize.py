@@ -98,3 +98,17 @@ def test_chunked_engine_is_bit_identical_at_full_size():
     a, _ = _tokens(small, frames, audio)                            # 128 frames in chunks of 48, 128 segments in 40s
     b, _ = _tokens(big, frames, audio)
     assert torch.equal(a, b)
+
+
+def test_graphed_step_is_bit_identical_and_reusable(full_path):
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import synthetic as S
+    B = 4
+    g = agb.GraphedClipBatch(full_path, B, 8, 8, device=DEV)
+    assert g.kernels_per_replay > 300
+    for seed in (61, 62):                                           # two different batches through the same graph
+        frames, audio = S.frames(B, 8, seed=seed).to(DEV), S.audio(B, 8, seed=seed + 10).to(DEV)
+        out = g(frames, audio)
+        want, _ = _tokens(full_path, frames, audio)
+        got = torch.cat([out["multi"], out["audio"], out["frame"]], dim=1)
+        assert torch.equal(got, want), seed
