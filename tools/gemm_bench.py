@@ -46,3 +46,21 @@ for name, M, N, K, act, resid in shapes:
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 os.makedirs(out, exist_ok=True)
 json.dump(res, open(os.path.join(out, f"gemm_bench_cg{os.environ.get('AGB_GEMM_CTA_GROUP', '2')}.json"), "w"), indent=1)
+
+# grouped positional conv (k = 128, 16 groups of 64): 512 sequences of 99 frames, resid += gelu(conv)
+nseq, stride, valid = 512, 100, 99
+x16 = torch.randn(nseq * stride, 1024, device=dev).to(torch.bfloat16)
+wp = (torch.randn(1024, 8192, device=dev) * 0.01).to(torch.bfloat16)
+pb = torch.randn(1024, device=dev)
+resid = torch.zeros(nseq * stride, 1024, device=dev)
+for _ in range(3):
+    ops.posconv_residual(x16, wp, pb, resid, nseq, stride, valid)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ops.posconv_residual(x16, wp, pb, resid, nseq, stride, valid)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print(f"posconv   512 x 99 x 1024, k=128 g=16: {ms:.3f} ms  {2.0 * nseq * valid * 1024 * 64 * 128 / ms / 1e9:.0f} TFLOP/s", flush=True)
