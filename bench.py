@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel separately instead of replaying a CUDA graph")
+    ap.add_argument("--only-resident", action="store_true",
+                    help="profiling aid (tools/launch_list.sh): run the warm-up and the device-resident timed steps only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -268,6 +270,13 @@ def main():
     l0 = E.launch_count()
     ms_dev = timed(step_resident, args.steps)
     launches = (graphed[2].kernels_per_replay * args.steps) if use_graph else (E.launch_count() - l0)
+    if args.only_resident:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": total_clips * args.steps / (ms_dev / 1e3), "unit": "clips/s",
+                              "ms_per_step": ms_dev / args.steps, "note": "--only-resident: no e2e / roofline legs"}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     run_e2e(2)
     ms_e2e = timed(lambda: run_e2e(args.steps), 1)
     clk = clocks.stop() if rank == 0 else None
