@@ -74,6 +74,7 @@ struct agb_ctx {
   // ---- workspaces
   int64_t v_cap = 0;  // frames
   bf16 *v_apatch = nullptr, *v_xln = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_h1 = nullptr, *v_clsln = nullptr;
+  bf16 *v_qcls = nullptr, *v_acls = nullptr;   // pruned last block: CLS queries / CLS attention output [frames,1024]
   float *v_patch_out = nullptr, *v_resid = nullptr;
   int64_t h_cap = 0;  // segments
   bf16 *h_c0 = nullptr, *h_c1 = nullptr, *h_xln = nullptr, *h_qkv = nullptr, *h_attn = nullptr, *h_h1 = nullptr;
@@ -99,7 +100,12 @@ template <typename T>
 int dev_alloc(agb_ctx* c, T** p, size_t count, bool zero = true) {
   void* q = nullptr;
   AGB_CHECK_CUDA(cudaMalloc(&q, count * sizeof(T)));
-  if (zero) AGB_CHECK_CUDA(cudaMemset(q, 0, count * sizeof(T)));
+  if (zero) {
+    // the memset runs on the legacy default stream, which non-blocking streams (torch side streams) do not wait for:
+    // finish it before any caller stream can touch the buffer (allocation happens only when a workspace grows)
+    AGB_CHECK_CUDA(cudaMemset(q, 0, count * sizeof(T)));
+    AGB_CHECK_CUDA(cudaDeviceSynchronize());
+  }
   c->allocs.push_back(q);
   *p = static_cast<T*>(q);
   return 0;
@@ -362,7 +368,7 @@ void tap(agb_ctx* c, const std::string& name, const void* src, int64_t bytes, cu
 // ------------------------------------------------------------------------------------ workspaces
 int ensure_vit_ws(agb_ctx* c, int64_t frames) {
   if (frames <= c->v_cap) return 0;
-  void* old[] = {c->v_apatch, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, c->v_clsln, c->v_patch_out, c->v_resid};
+  void* old[] = {c->v_apatch, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, c->v_clsln, c->v_patch_out, c->v_resid, c->v_qcls, c->v_acls};
   for (void* p : old) dev_free(c, p);
   c->v_cap = 0;
   const size_t M = (size_t)frames * 257;
@@ -374,6 +380,8 @@ int ensure_vit_ws(agb_ctx* c, int64_t frames) {
   if (int r = dev_alloc(c, &c->v_attn, M * 1024)) return r;
   if (int r = dev_alloc(c, &c->v_h1, M * 4096)) return r;
   if (int r = dev_alloc(c, &c->v_clsln, (size_t)frames * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_qcls, (size_t)frames * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_acls, (size_t)frames * 1024)) return r;
   c->v_cap = frames;
   return 0;
 }
@@ -445,6 +453,37 @@ int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* 
   return gemm_bf16(g, s);
 }
 
+// Last ViT block when only the pooled CLS row is consumed (CLIPVisionTransformer: pooled_output = last_hidden_state[:, 0],
+// modeling_clip.py:685-686): LN1 and the K/V projection over all 257 rows, then Q, attention, out-proj, LN2 and the MLP for
+// the CLS row of each frame only (strided views of the residual stream: row pitch 257 * 1024).  Same arithmetic for that
+// row as the dense block; 5.66 of the block's 6.75 GFLOP per frame are not executed.
+int vit_last_block_cls(agb_ctx* c, const EncLayerW& L, int64_t F, cudaStream_t s) {
+  const int64_t M = F * 257, pitch = 257 * 1024;
+  if (int r = layernorm_f32_in(c->v_resid, 1024, M, 1024, L.lnA_g, L.lnA_b, 1e-5f, c->v_xln, 1024, nullptr, 0, s)) return r;
+  GemmArgs g;
+  g.A = c->v_xln; g.lda = 1024; g.W = L.wqkv + 1024ull * 1024; g.M = (int)M; g.N = 2048; g.K = 1024; g.bias = L.bqkv + 1024;
+  g.out_bf16 = c->v_qkv + 1024; g.ld_bf16 = 3072;
+  if (int r = gemm_bf16(g, s)) return r;
+  g = GemmArgs();
+  g.A = c->v_xln; g.lda = pitch; g.W = L.wqkv; g.M = (int)F; g.N = 1024; g.K = 1024; g.bias = L.bqkv;
+  g.out_bf16 = c->v_qcls; g.ld_bf16 = 1024;
+  if (int r = gemm_bf16(g, s)) return r;
+  if (int r = vit_cls_attention(c->v_qcls, c->v_qkv, F, 0.125f, c->v_acls, s)) return r;
+  g = GemmArgs();
+  g.A = c->v_acls; g.lda = 1024; g.W = L.wo; g.M = (int)F; g.N = 1024; g.K = 1024; g.bias = L.bo;
+  g.res = c->v_resid; g.ld_res = pitch; g.out_f32 = c->v_resid; g.ld_f32 = pitch;
+  if (int r = gemm_bf16(g, s)) return r;
+  if (int r = layernorm_f32_in(c->v_resid, pitch, F, 1024, L.lnB_g, L.lnB_b, 1e-5f, c->v_clsln, 1024, nullptr, 0, s)) return r;
+  g = GemmArgs();
+  g.A = c->v_clsln; g.lda = 1024; g.W = L.w1; g.M = (int)F; g.N = 4096; g.K = 1024; g.bias = L.b1; g.act = ACT_QUICK_GELU;
+  g.out_bf16 = c->v_h1; g.ld_bf16 = 4096;
+  if (int r = gemm_bf16(g, s)) return r;
+  g = GemmArgs();
+  g.A = c->v_h1; g.lda = 4096; g.W = L.w2; g.M = (int)F; g.N = 1024; g.K = 4096; g.bias = L.b2;
+  g.res = c->v_resid; g.ld_res = pitch; g.out_f32 = c->v_resid; g.ld_f32 = pitch;
+  return gemm_bf16(g, s);
+}
+
 int clip_chunk(agb_ctx* c, const void* frames, int in_dtype, int64_t F, float* out, cudaStream_t s) {
   const int64_t M = F * 257;
   if (int r = vit_patchify(frames, in_dtype, F, c->v_apatch, s)) return r;
@@ -454,7 +493,14 @@ int clip_chunk(agb_ctx* c, const void* frames, int in_dtype, int64_t F, float* o
   if (int r = gemm_bf16(g, s)) return r;
   if (int r = vit_embed_preln(c->v_patch_out, c->v_cls, c->v_pos, c->v_pre_g, c->v_pre_b, 1e-5f, F, c->v_resid, s)) return r;
   tap(c, "vit.embed", c->v_resid, M * 1024 * 4, s);
+  // the last block is pruned to the CLS row unless the caller wants it dense (cfg) or taps its full output
+  const int last = c->cfg.vit_layers - 1;
+  const bool dense_last = c->cfg.vit_dense_last_block != 0 || c->taps.count("vit.block" + std::to_string(last)) != 0;
   for (int l = 0; l < c->cfg.vit_layers; ++l) {
+    if (l == last && !dense_last) {
+      if (int r = vit_last_block_cls(c, c->v_layers[l], F, s)) return r;
+      break;
+    }
     if (int r = encoder_block(c->v_layers[l], c->v_resid, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, M, (int)F, 257, 257,
                               ACT_QUICK_GELU, s))
       return r;
@@ -572,6 +618,7 @@ int agb_create(agb_ctx** out, int device, const agb_cfg* cfg) {
   if (c->cfg.llm_dim <= 0) c->cfg.llm_dim = 3584;
   if (c->cfg.max_frames_per_chunk <= 0) c->cfg.max_frames_per_chunk = 512;
   if (c->cfg.max_segments_per_chunk <= 0) c->cfg.max_segments_per_chunk = 512;
+  if (const char* e = getenv("AGB_VIT_DENSE_LAST")) c->cfg.vit_dense_last_block = e[0] == '1';   // A/B switch (bench, tools)
   if (c->cfg.hubert_layers < 3) { set_error("agb_create: hubert_layers must be >= 3 (last-4 hidden states)"); delete c; return 2; }
   if (int r = register_weights(c)) { agb_destroy(c); return r; }
   *out = c;

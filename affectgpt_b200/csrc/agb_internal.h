@@ -108,6 +108,10 @@ int vit_embed_preln(const float* patch_out /*[n*256,1024]*/, const float* cls, c
                     const float* g, const float* b, float eps, int64_t nframes, float* resid /*[n*257,1024]*/,
                     cudaStream_t s);
 
+// last block only: softmax(q_cls K^T * scale) V for the CLS query of each frame; q_cls [n,1024], qkv [n*257,3072] (K, V
+// columns filled), out [n,1024]
+int vit_cls_attention(const bf16* q_cls, const bf16* qkv, int64_t nframes, float scale, bf16* out, cudaStream_t s);
+
 // hubert.cu ----------------------------------------------------------------------------------
 int wave_stats(const float* wav, int64_t nseg, int64_t samples, int64_t seg_per_group, float* stats /*[ngroups,2] mean,rstd*/,
                int do_normalize, double* acc_scratch /*[ngroups,2]*/, cudaStream_t s);

@@ -92,6 +92,81 @@ __global__ void __launch_bounds__(256) embed_preln_kernel(const float* __restric
   }
 }
 
+// CLS-query attention of the LAST encoder block: CLIPVisionTransformer pools hidden_state[:, 0] only
+// (modeling_clip.py:685-686), so after the last block's K/V projection every other query row is dead work.
+// One warp per (frame, head): lanes split the 257 keys for the scores (each lane reads whole 128-byte K rows), exact
+// fp32 softmax across the warp, then lanes split the 64 output dims for P.V (coalesced 128-byte V rows).
+__global__ void __launch_bounds__(512) cls_attention_kernel(const bf16* __restrict__ q_cls /*[F,1024]*/,
+                                                           const bf16* __restrict__ qkv /*[F*257,3072]*/, int nframes,
+                                                           float scale, bf16* __restrict__ out /*[F,1024]*/) {
+  constexpr int T = 257, KPL = 9;                       // keys per lane: ceil(257 / 32)
+  __shared__ float sp[16][T + 3];
+  const int frame = blockIdx.x, head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (frame >= nframes) return;
+  const bf16* kbase = qkv + (size_t)frame * T * 3072 + 1024 + head * 64;
+  const bf16* vbase = kbase + 1024;
+  float q[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q_cls + (size_t)frame * 1024 + head * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = __ldg(qp + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        q[i * 8 + e * 2] = f.x * scale;
+        q[i * 8 + e * 2 + 1] = f.y * scale;
+      }
+    }
+  }
+  float sc[KPL];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int key = lane + 32 * j;
+    float acc = -INFINITY;
+    if (key < T) {
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + (size_t)key * 3072);
+      acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = __ldg(kp + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          acc = fmaf(q[i * 8 + e * 2], f.x, acc);
+          acc = fmaf(q[i * 8 + e * 2 + 1], f.y, acc);
+        }
+      }
+    }
+    sc[j] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int key = lane + 32 * j;
+    const float e = key < T ? __expf(sc[j] - mx) : 0.f;
+    if (key < T) sp[head][key] = e;
+    sum += e;
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+  const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(vbase) + lane;
+#pragma unroll 4
+  for (int key = 0; key < T; ++key) {
+    const float2 f = __bfloat1622float2(__ldg(vp + (size_t)key * (3072 / 2)));
+    const float pk = sp[head][key];
+    o0 = fmaf(pk, f.x, o0);
+    o1 = fmaf(pk, f.y, o1);
+  }
+  reinterpret_cast<__nv_bfloat162*>(out + (size_t)frame * 1024 + head * 64)[lane] = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+}
+
 }  // namespace
 
 int vit_patchify(const void* frames, int in_dtype, int64_t nframes, bf16* a_patch, cudaStream_t s) {
@@ -115,6 +190,14 @@ int vit_embed_preln(const float* patch_out, const float* cls, const float* pos, 
   const long long rows = nframes * 257;
   LaunchTimer timer(PROF_LAYERNORM, 8.0 * rows * 1024, (double)rows * 1024 * 8.0, s);
   embed_preln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(patch_out, cls, pos, g, b, eps, nframes, resid);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
+
+int vit_cls_attention(const bf16* q_cls, const bf16* qkv, int64_t nframes, float scale, bf16* out, cudaStream_t s) {
+  AGB_REQUIRE(nframes > 0, "cls attention: no frames");
+  LaunchTimer timer(PROF_ATTENTION, 4.0 * nframes * 16 * 257 * 64, (double)nframes * 257 * 2048 * 2.0, s);
+  cls_attention_kernel<<<(unsigned)nframes, 512, 0, s>>>(q_cls, qkv, (int)nframes, scale, out);
   AGB_CHECK_LAUNCH();
   return 0;
 }

@@ -31,7 +31,7 @@ class Engine:
     def __init__(self, device="cuda:0", vit_layers: int = 24, hubert_layers: int = 24,
                  feat_extract_norm: str = "layer", do_normalize: bool = True, llm_dim: int = 3584,
                  max_frames_per_chunk: int = 512, max_segments_per_chunk: int = 512, qf_video_queries: int = 0,
-                 qf_audio_queries: int = 0, qf_multi_queries: int = 0):
+                 qf_audio_queries: int = 0, qf_multi_queries: int = 0, vit_dense_last_block: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("affectgpt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if feat_extract_norm not in ("layer", "group"):
@@ -49,6 +49,7 @@ class Engine:
         cfg.hubert_conv_norm = 0 if feat_extract_norm == "layer" else 1
         cfg.hubert_do_normalize = 1 if do_normalize else 0
         cfg.llm_dim = llm_dim
+        cfg.vit_dense_last_block = 1 if vit_dense_last_block else 0
         cfg.max_frames_per_chunk = max_frames_per_chunk
         cfg.max_segments_per_chunk = max_segments_per_chunk
         cfg.qf_video_queries, cfg.qf_audio_queries, cfg.qf_multi_queries = qf_video_queries, qf_audio_queries, qf_multi_queries

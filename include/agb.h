@@ -42,7 +42,9 @@ typedef struct agb_cfg {
   int32_t qf_video_queries;       /* num_video_query_token when video_fusion_type == "qformer", else 0 (not built) */
   int32_t qf_audio_queries;       /* num_audio_query_token when audio_fusion_type == "qformer", else 0 */
   int32_t qf_multi_queries;       /* num_multi_query_token when multi_fusion_type == "qformer", else 0 */
-  int32_t reserved[6];
+  int32_t vit_dense_last_block;   /* 0 (default): the last ViT block computes only what the pooled CLS row needs (K/V for all
+                                     tokens, everything else for the CLS row); 1: all 257 rows, as the reference does */
+  int32_t reserved[5];
 } agb_cfg;
 
 enum { AGB_DTYPE_F32 = 0, AGB_DTYPE_U8 = 1, AGB_DTYPE_BF16 = 2 };

@@ -44,6 +44,32 @@ def test_vit_small_with_per_block_taps(small_path):
     assert R.nn_identity(got.cpu(), want)
 
 
+def test_vit_pruned_last_block_matches_dense_block(small_path):
+    """Default: the last ViT block runs K/V for all tokens but Q / attention / out-proj / MLP for the pooled CLS row only
+    (CLIPVisionTransformer pools hidden[:, 0], modeling_clip.py:685-686).  It must agree with the dense block, and both
+    with the oracle; a tap on the last block switches that call to the dense block (all 257 rows valid)."""
+    import affectgpt_b200 as agb
+    model, clip, _, _ = small_path
+    raw = R.synth_frames(2, 4, seed=5)
+    frames = raw.permute(0, 2, 1, 3, 4).reshape(8, 3, 224, 224).to(DEV)
+    pruned = model._engine.clip_forward(frames)
+    dense_eng = agb.Engine(DEV, vit_layers=2, hubert_layers=3, vit_dense_last_block=True)
+    dense_eng.load_state_dict("clip", clip.state_dict())
+    dense = dense_eng.clip_forward(frames)
+    dense_eng.close()
+    gate(pruned, dense, "pruned vs dense last block", cos_min=0.99999, rel_max=2e-3)
+    with torch.no_grad():
+        want = clip(pixel_values=R.clip_preprocess(raw)).image_embeds
+    gate(pruned, want, "pruned vs oracle")
+    gate(dense, want, "dense vs oracle")
+    tap = model._engine.tap("vit.block1", (8 * 257, 1024))
+    tapped = model._engine.clip_forward(frames)
+    model._engine.clear_taps()
+    assert torch.equal(tapped, dense)                                               # tap => dense block, bit for bit
+    assert float(tap.reshape(8, 257, 1024)[:, 1:].abs().max()) > 0
+    assert torch.equal(model._engine.clip_forward(frames), pruned)                  # deterministic, back to pruned
+
+
 def test_vit_u8_input_and_chunking_are_bit_identical(small_path):
     import affectgpt_b200 as agb
     model, clip, _, _ = small_path
@@ -131,6 +157,29 @@ def test_fusion_heads_and_projectors(small_path):
     assert rel_err(vm, R.encode_video_attention(fus, fh, fusion_type="mean")[1]) < 1e-4
     _, am = m2.encode_audio_merge(ah.to(DEV), None, is_preextracted=True)
     assert rel_err(am, R.encode_audio_attention(fus, ah, fusion_type="mean")[1]) < 1e-4
+
+
+def test_two_stream_encoder_overlap_is_bit_identical(small_path):
+    """encode_clip_batch issues the audio chain on a side stream (joined before the heads): same kernels, same inputs,
+    so every output equals the single-stream run bit for bit - eagerly and when replayed from a captured graph."""
+    import affectgpt_b200 as agb
+    model = small_path[0]
+    s = {"raw_frames": R.synth_frames(2, 3, seed=7).to(DEV), "raw_faces": R.synth_frames(2, 3, seed=8).to(DEV),
+         "raw_audios": R.synth_audio(2, 2, seed=9).to(DEV)}
+    was = model.overlap_encoders
+    model.overlap_encoders = True
+    try:
+        a = {k: v.clone() for k, v in model.encode_clip_batch(s).items()}
+        g = agb.GraphedClipBatch(model, 2, 3, 2, with_faces=True, device=DEV)
+        c = {k: v.clone() for k, v in g(s["raw_frames"], s["raw_audios"], s["raw_faces"]).items()}
+        model.overlap_encoders = False
+        b = model.encode_clip_batch(s)
+        torch.cuda.synchronize()
+        assert set(a) == set(b) == set(c)
+        for k in a:
+            assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+    finally:
+        model.overlap_encoders = was
 
 
 def test_encode_clip_batch_token_set(small_path):
