@@ -16,7 +16,9 @@ Same command line (``--dataset --modality --video_root --face_root --audio_root 
 * the loaders the directories are read by: A/my_affectgpt/datasets/datasets/base_dataset.py:392-405, 481-492, 520-531.
 
 What differs is where the work runs: frames, face crops and audio segments are staged on the GPU (``staging``), the
-encoders and fusion heads are the sm_100a kernels behind the C ABI, and samples are batched per launch.  Under
+encoders and fusion heads are the sm_100a kernels behind the C ABI, and ``--batch_size`` samples (default 32) share one
+ViT call and one HuBERT call while a thread pool decodes the next batch and writes the previous one
+(``run_sweep_batched``; ``--batch_size 1`` is the reference's per-sample loop, ``run_sweep``).  Under
 ``torchrun`` each rank takes samples ``rank::world_size`` and writes its own files - no collective (SURVEY 8e, C5).
 Decoding (mp4 / wav) is outside the path: videos are read with decord when it is installed, else OpenCV, else a
 pre-decoded ``<video_root>/<name>.npy`` uint8 stack ``[N,h,w,3]`` (RGB); wavs with scipy.
@@ -129,6 +131,8 @@ class MultimodalFeatureExtractor:
         self.encoders = {"visual": visual_encoder, "acoustic": acoustic_encoder}
         self.multi_fusion_model = fusion
         self.mer_factory_output = mer_factory_output
+        self._side = None                                      # staging stream of run_sweep_batched
+        self._pinned, self._pinned_busy, self._pinned_turn = [None, None], [None, None], 0
 
     # ---- single-sample calls, reference signatures
     def extract_frame_features(self, video_path, n_frms=8, sampling="uniform", video_name=None):
@@ -171,6 +175,151 @@ class MultimodalFeatureExtractor:
         except Exception as e:
             print(f"Error extracting multi features: {e}")
             return None
+
+    # ---- batched calls (run_sweep_batched).  Host decoding (pool threads) -> prestage (H2D + device staging of a whole
+    # batch on a side stream) -> submit (encoders + multi head, asynchronous on the calling stream) -> collect (D2H).
+    # The sweep prestages batch k+1 between submit(k) and collect(k), so copies and staging kernels overlap the encoders.
+    def decode_frames(self, video_path, n_frms=8, sampling="uniform", video_name=None) -> Optional[np.ndarray]:
+        """-> uint8 [T,224,224,3] (host)."""
+        try:
+            return read_video_frames(video_path, lambda vlen: frame_indices(vlen, n_frms, sampling, video_name,
+                                                                            self.mer_factory_output))
+        except Exception as e:
+            print(f"Error extracting frame features from {video_path}: {e}")
+            return None
+
+    def decode_faces(self, face_npy_path, n_frms=8) -> Optional[np.ndarray]:
+        """-> uint8 [n_frms,h,w,3] (host): only the sampled crops travel to the device."""
+        try:
+            faces = np.load(face_npy_path, mmap_mode="r")
+            idx = sampling.uniform_frame_indices(len(faces), n_frms)
+            return np.ascontiguousarray(faces[idx])
+        except Exception as e:
+            print(f"Error extracting face features from {face_npy_path}: {e}")
+            return None
+
+    def decode_audio(self, audio_path) -> Optional[torch.Tensor]:
+        """-> float32 [channels, n] at 16 kHz (host)."""
+        try:
+            return read_wav(audio_path)
+        except Exception:
+            return None
+
+    def prestage(self, decoded: List[dict], clips_per_video: int = 8) -> dict:
+        """decoded[i] = {'frame': u8 [T,224,224,3], 'face': u8 [8,h,w,3], 'audio': wav [ch,n]} (any subset) -> device
+        tensors of the whole batch, produced on a side stream: frames in ONE pinned-buffer copy, face crops resized
+        there (cv2-exact), audio mixed down / padded / sliced there.  A sample whose staging fails becomes None."""
+        dev = self.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        n = len(decoded)
+        st = {"n": n, "frame_owner": [], "face_owner": [], "audio_owner": [], "frames": None, "faces": None, "audio": None}
+        with torch.cuda.device(dev), torch.cuda.stream(self._side):
+            fr = [(i, d["frame"]) for i, d in enumerate(decoded) if d.get("frame") is not None]
+            if fr:
+                total = sum(f.shape[0] for _, f in fr)
+                slot = self._pinned_slot(total)
+                off = 0
+                for i, f in fr:
+                    slot[off:off + f.shape[0]].numpy()[...] = f
+                    st["frame_owner"].append((i, f.shape[0]))
+                    off += f.shape[0]
+                st["frames"] = slot[:total].to(dev, non_blocking=True).permute(0, 3, 1, 2).contiguous()
+                self._pinned_busy[self._pinned_turn].record(self._side)
+            faces = []
+            for i, d in enumerate(decoded):
+                if d.get("face") is None:
+                    continue
+                try:
+                    faces.append(staging.stage_faces(d["face"], list(range(len(d["face"]))), dev))
+                    st["face_owner"].append((i, faces[-1].shape[0]))
+                except Exception as e:
+                    print(f"Error staging face crops of sample {i}: {e}")
+            if faces:
+                st["faces"] = torch.cat(faces, dim=0)
+            segs = []
+            for i, d in enumerate(decoded):
+                if d.get("audio") is None:
+                    continue
+                try:
+                    segs.append(staging.stage_audio(d["audio"], clips_per_video=clips_per_video, device=dev))
+                    st["audio_owner"].append(i)
+                except Exception:
+                    pass
+            if segs:
+                st["audio"] = torch.stack(segs, dim=0)
+            st["ready"] = torch.cuda.Event()
+            st["ready"].record(self._side)
+        return st
+
+    def _pinned_slot(self, frames: int) -> torch.Tensor:
+        """Two pinned uint8 [frames,224,224,3] upload slots used alternately; a slot is rewritten only after the copy
+        that last read it has finished."""
+        self._pinned_turn ^= 1
+        t = self._pinned_turn
+        if self._pinned[t] is None or self._pinned[t].shape[0] < frames:
+            self._pinned[t] = torch.empty((frames, 224, 224, 3), dtype=torch.uint8).pin_memory()
+            self._pinned_busy[t] = torch.cuda.Event()
+        else:
+            self._pinned_busy[t].synchronize()
+        return self._pinned[t]
+
+    def submit_batch(self, staged: dict, multi_of: List[int]) -> dict:
+        """Encoders over everything staged (ONE ViT call for all frames and face crops, ONE HuBERT call) and the multi
+        head for the samples listed in ``multi_of`` that have both face and audio features; asynchronous on the current
+        stream.  Returns device tensors; ``collect_batch`` brings them to the host."""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(staged["ready"])
+        h = {"staged": staged, "visual": None, "audio": None, "multi": None, "multi_idx": []}
+        parts = [t for t in (staged["frames"], staged["faces"]) if t is not None]
+        for t in parts + ([staged["audio"]] if staged["audio"] is not None else []):
+            t.record_stream(cur)                                   # allocated on the side stream, read here
+        with torch.no_grad():
+            if parts:
+                allf = torch.cat(parts, dim=0) if len(parts) > 1 else parts[0]
+                enc = self.encoders["visual"]
+                h["visual"] = (enc._ensure_engine(dev).clip_forward(allf) if hasattr(enc, "_ensure_engine")
+                               else enc(None, allf.permute(1, 0, 2, 3)[None].float())[0])
+            if staged["audio"] is not None:
+                h["audio"] = self.encoders["acoustic"](None, staged["audio"])                     # [n,clips,1024]
+            n_frame = sum(t for _, t in staged["frame_owner"])
+            face_row, off = {}, n_frame
+            for i, t in staged["face_owner"]:
+                face_row[i] = (off, t)
+                off += t
+            audio_row = {i: j for j, i in enumerate(staged["audio_owner"])}
+            idx = [i for i in multi_of if i in face_row and i in audio_row]
+            if idx:
+                if self.multi_fusion_model is None:
+                    raise RuntimeError("Multi fusion model not loaded.")
+                f = torch.stack([h["visual"][face_row[i][0]:face_row[i][0] + face_row[i][1]] for i in idx])
+                a = torch.stack([h["audio"][audio_row[i]] for i in idx])
+                h["multi"], _ = self.multi_fusion_model.encode_multi_merge(f, a)
+                h["multi_idx"] = idx
+        return h
+
+    def collect_batch(self, h: dict):
+        """-> (frame feats, face feats, audio feats, multi feats): lists over the batch of fp32 numpy arrays or None."""
+        st = h["staged"]
+        n = st["n"]
+        ff, cf, af, mf = [None] * n, [None] * n, [None] * n, [None] * n
+        if h["visual"] is not None:
+            v = h["visual"].float().cpu().numpy()
+            off = 0
+            for owners, dst in ((st["frame_owner"], ff), (st["face_owner"], cf)):
+                for i, t in owners:
+                    dst[i] = v[off:off + t].copy()
+                    off += t
+        if h["audio"] is not None:
+            a = h["audio"].float().cpu().numpy()
+            for j, i in enumerate(st["audio_owner"]):
+                af[i] = a[j].copy()
+        if h["multi"] is not None:
+            m = h["multi"].float().cpu().numpy()
+            for j, i in enumerate(h["multi_idx"]):
+                mf[i] = m[j].copy()
+        return ff, cf, af, mf
 
     # ---- helpers
     def _visual(self, u8_btchw: torch.Tensor) -> np.ndarray:
@@ -278,6 +427,136 @@ def run_sweep(args, extractor, sample_names: List[str], log=print) -> Dict[str, 
     return stats
 
 
+def run_sweep_batched(args, extractor, sample_names: List[str], batch_size: int = 32, workers: int = 8,
+                      log=print) -> Dict[str, int]:
+    """Same files, same statistics and same per-sample failure rules as ``run_sweep``, but the device sees batches:
+    a thread pool decodes and stages the next batch (and writes the previous one) while the GPU encodes, all frames and face crops of ``batch_size`` samples
+    go through ONE ViT call and all their audio segments through ONE HuBERT call, and in ``--modality all`` the multi
+    features reuse the face / audio features of the same pass (the reference extracts them a second time, :1001-1003;
+    the encoders are deterministic and batch-invariant bit for bit, so the files are identical).  If the device work
+    of a batch raises, that batch is redone sample by sample through ``run_sweep`` so one bad sample cannot take its
+    neighbours with it."""
+    from concurrent.futures import ThreadPoolExecutor
+    dirs = save_dirs(args)
+    keys = ("frame_success", "face_success", "audio_success", "audio_failed", "multi_success", "multi_failed",
+            "skipped_existing")
+    stats = {k: 0 for k in keys}
+    quiet = args.quiet
+    want_audio_file = args.modality in ("audio", "all")
+
+    def plan(name):
+        """Which outputs are missing for this sample and which sources have to be decoded for them."""
+        j = {"name": name, "skipped": 0, "out": {}, "src": {}, "notes": []}
+        video = os.path.join(args.video_root, f"{name}.mp4") if args.video_root else None
+        face_npy = os.path.join(args.face_root, name, f"{name}.npy") if args.face_root else None
+        wav = os.path.join(args.audio_root, f"{name}.wav") if args.audio_root else None
+        for kind in ("frame", "face", "audio", "multi"):
+            if kind not in dirs or (kind == "audio" and not want_audio_file):
+                continue
+            out = os.path.join(dirs[kind], f"{name}.npy")
+            if os.path.exists(out):
+                j["skipped"] += 1
+            else:
+                j["out"][kind] = out
+        if "frame" in j["out"]:
+            if os.path.exists(video) or os.path.exists(os.path.splitext(video)[0] + ".npy"):
+                j["src"]["frame"] = video
+            else:
+                del j["out"]["frame"]
+        has_face, has_wav = bool(face_npy) and os.path.exists(face_npy), bool(wav) and os.path.exists(wav)
+        if "face" in j["out"] and not has_face:
+            del j["out"]["face"]
+            j["notes"].append(f"Face: {name} -> file not found: {face_npy}")
+        if has_face and ("face" in j["out"] or "multi" in j["out"]):
+            j["src"]["face"] = face_npy
+        if has_wav and ("audio" in j["out"] or "multi" in j["out"]):
+            j["src"]["audio"] = wav
+        return j
+
+    def decode(j):
+        d = {}
+        if "frame" in j["src"]:
+            d["frame"] = extractor.decode_frames(j["src"]["frame"], args.frame_n_frms, args.frame_sampling, j["name"])
+        if "face" in j["src"]:
+            d["face"] = extractor.decode_faces(j["src"]["face"], 8)
+        if "audio" in j["src"]:
+            d["audio"] = extractor.decode_audio(j["src"]["audio"])
+        return d
+
+    def finish(jobs, handle):
+        """-> per job {kind: array} of everything that has to be written, plus the batch's statistics."""
+        st = {k: 0 for k in keys}
+        ff, cf, af, mf = extractor.collect_batch(handle)
+        writes = []
+        for i, j in enumerate(jobs):
+            st["skipped_existing"] += j["skipped"]
+            w, name = {}, j["name"]
+            for note in j["notes"]:
+                if not quiet:
+                    log(note)
+            if "frame" in j["out"] and ff[i] is not None:
+                w["frame"] = ff[i]; st["frame_success"] += 1
+            if "face" in j["out"] and cf[i] is not None:
+                w["face"] = cf[i]; st["face_success"] += 1
+            if "audio" in j["out"]:
+                if af[i] is not None:
+                    w["audio"] = af[i]; st["audio_success"] += 1
+                else:                                              # missing file or failed processing (:965-975)
+                    w["audio"] = np.zeros((args.clips_per_video, 1024), dtype=np.float32); st["audio_failed"] += 1
+            if "multi" in j["out"]:
+                if mf[i] is not None:
+                    w["multi"] = mf[i]; st["multi_success"] += 1
+                else:
+                    st["multi_failed"] += 1
+            if not quiet:
+                for kind, arr in w.items():
+                    log(f"{kind.capitalize()}: {name} -> " + ("zero-padded" if kind == "audio" and af[i] is None else f"{arr.shape}"))
+            writes.append(w)
+        return writes, st
+
+    batches = [sample_names[i:i + batch_size] for i in range(0, len(sample_names), batch_size)]
+    pending_writes = []
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+        def submit_decode(names):
+            jobs = [plan(n) for n in names]
+            return jobs, [pool.submit(decode, j) for j in jobs]
+
+        def staged_of(item):
+            """Wait for the pool, then copy + stage the batch on the side stream; an exception is kept for the consumer."""
+            jobs, futs = item
+            try:
+                return jobs, extractor.prestage([f.result() for f in futs], args.clips_per_video)
+            except Exception as e:
+                return jobs, e
+
+        queue = [submit_decode(b) for b in batches[:2]]             # decode two batches ahead of the device
+        cur = staged_of(queue.pop(0)) if queue else None
+        for b in range(len(batches)):
+            jobs, staged = cur
+            if b + 2 < len(batches):
+                queue.append(submit_decode(batches[b + 2]))
+            try:
+                if isinstance(staged, Exception):
+                    raise staged
+                handle = extractor.submit_batch(staged, [i for i, j in enumerate(jobs) if "multi" in j["out"]])
+                cur = staged_of(queue.pop(0)) if queue else None     # next batch's H2D + staging overlap these encoders
+                writes, st = finish(jobs, handle)
+            except Exception as e:
+                log(f"batch of {len(jobs)} failed on the device ({e}); redoing it sample by sample")
+                st = run_sweep(args, extractor, [j["name"] for j in jobs], log=log)
+                writes = []
+                if cur is not None and cur[0] is jobs:
+                    cur = staged_of(queue.pop(0)) if queue else None
+            for j, w in zip(jobs, writes):
+                for kind, arr in w.items():
+                    pending_writes.append(pool.submit(np.save, j["out"][kind], arr))
+            for k in keys:
+                stats[k] += st[k]
+        for f in pending_writes:
+            f.result()
+    return stats
+
+
 def read_sample_names(args) -> List[str]:
     """--sample_list (one name per line) or --csv_path / --csv_column (:1120-1123 and the csv branch)."""
     if bool(args.sample_list) == bool(args.csv_path):
@@ -313,6 +592,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--clips_per_video", type=int, default=8)
     p.add_argument("--n_frms", type=int, default=8, help="Deprecated: use --frame_n_frms instead")
     p.add_argument("--fusion_ckpt", type=str, help="AffectGPT checkpoint (ckpt['model']) for the multi features")
+    p.add_argument("--batch_size", type=int, default=32,
+                   help="samples per device batch (not in the reference, which runs one sample per call); 1 = the "
+                        "reference's per-sample loop")
+    p.add_argument("--workers", type=int, default=8, help="host threads decoding / writing around the device batches")
     return p
 
 
@@ -352,7 +635,10 @@ def main(argv: Optional[List[str]] = None) -> int:
         fusion.load_state_dict(ckpt.get("model", ckpt))
     extractor = MultimodalFeatureExtractor(visual, acoustic, fusion, device=args.device,
                                            mer_factory_output=args.mer_factory_output)
-    stats = run_sweep(args, extractor, names)
+    if args.batch_size > 1:
+        stats = run_sweep_batched(args, extractor, names, batch_size=args.batch_size, workers=args.workers)
+    else:
+        stats = run_sweep(args, extractor, names)
     print(f"[rank {rank}/{world}] " + ", ".join(f"{k}={v}" for k, v in stats.items()))
     return 0
 

@@ -117,3 +117,90 @@ def test_csv_sample_source_and_frame_index_rules(tmp_path):
     assert X.frame_indices(88, 8, "uniform") == [0, 11, 22, 33, 44, 55, 66, 77]
     assert X.frame_indices(88, 8, "emotion_peak") == [44] * 8
     assert X.frame_indices(5, 8, "uniform") == [0, 1, 2, 3, 4, 4, 4, 4]
+
+
+class BatchStub(StubExtractor):
+    """The batched surface of MultimodalFeatureExtractor over the same fake features as StubExtractor."""
+
+    def decode_frames(self, video_path, n_frms=8, sampling="uniform", video_name=None):
+        self.calls.append(("frame", video_name, n_frms, sampling))
+        return np.zeros((n_frms, 2, 2, 3), np.uint8)
+
+    def decode_faces(self, face_npy_path, n_frms=8):
+        self.calls.append(("face", os.path.basename(face_npy_path), n_frms))
+        return np.zeros((n_frms, 2, 2, 3), np.uint8)
+
+    def decode_audio(self, audio_path):
+        self.calls.append(("audio", os.path.basename(audio_path)))
+        return None if "broken" in audio_path else np.zeros((1, 4), np.float32)
+
+    def prestage(self, decoded, clips_per_video=8):
+        return {"decoded": decoded, "clips": clips_per_video}
+
+    def submit_batch(self, staged, multi_of):
+        d = staged["decoded"]
+        self.calls.append(("visual_batch", sum(x.get("frame") is not None for x in d), sum(x.get("face") is not None for x in d)))
+        return {"staged": staged, "multi_of": multi_of}
+
+    def collect_batch(self, h):
+        d, c = h["staged"]["decoded"], h["staged"]["clips"]
+        ff = [None if x.get("frame") is None else np.full((len(x["frame"]), 768), 1.0, np.float32) for x in d]
+        cf = [None if x.get("face") is None else np.full((len(x["face"]), 768), 2.0, np.float32) for x in d]
+        af = [None if x.get("audio") is None else np.full((c, 1024), 3.0, np.float32) for x in d]
+        mf = [np.full((1024,), 4.0, np.float32) if (i in h["multi_of"] and cf[i] is not None and af[i] is not None) else None
+              for i in range(len(d))]
+        return ff, cf, af, mf
+
+
+def _tree(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            out[os.path.relpath(os.path.join(d, f), root)] = np.load(os.path.join(d, f))
+    return out
+
+
+@pytest.mark.parametrize("modality", ["all", "multi", "face", "audio"])
+def test_batched_sweep_writes_what_the_per_sample_sweep_writes(tmp_path, modality):
+    """run_sweep_batched (device batches + decode-ahead thread pool) == run_sweep (the reference's loop): same files,
+    same contents, same statistics - including zero-filled audio, missing sources, and a resumed second pass."""
+    names = ["s1", "broken", "noaudio", "s4", "s5"]
+    argv = _dataset(tmp_path, names) + ["--modality", modality]
+    (tmp_path / "face" / "s4" / "s4.npy").unlink()                       # a sample without face crops
+    results = []
+    for mode in ("single", "batched"):
+        a = X.build_parser().parse_args(argv[:argv.index("--save_root") + 1] + [str(tmp_path / mode)] +
+                                        argv[argv.index("--save_root") + 2:])
+        X.validate_args(a)
+        ex = BatchStub()
+        if mode == "single":
+            st = X.run_sweep(a, ex, names + ["ghost"], log=lambda *_: None)
+        else:
+            st = X.run_sweep_batched(a, ex, names + ["ghost"], batch_size=2, workers=3, log=lambda *_: None)
+            if modality == "all":                                        # frames and faces of a batch share one encoder call
+                assert ("visual_batch", 2, 2) in ex.calls
+        results.append((st, _tree(tmp_path / mode)))
+    (st_a, tree_a), (st_b, tree_b) = results
+    assert st_a == st_b
+    assert sorted(tree_a) == sorted(tree_b) and len(tree_a) > 0
+    for k in tree_a:
+        assert tree_a[k].dtype == tree_b[k].dtype and np.array_equal(tree_a[k], tree_b[k]), k
+    a = X.build_parser().parse_args(argv[:argv.index("--save_root") + 1] + [str(tmp_path / "batched")] +
+                                    argv[argv.index("--save_root") + 2:])
+    st2 = X.run_sweep_batched(a, BatchStub(), names + ["ghost"], batch_size=4, log=lambda *_: None)   # resume
+    assert st2["frame_success"] == st2["face_success"] == st2["audio_success"] == st2["multi_success"] == 0
+    assert st2["skipped_existing"] == len(tree_b)
+
+
+@pytest.mark.parametrize("bs", [1, 2])
+def test_batched_sweep_falls_back_per_sample_when_the_device_batch_raises(tmp_path, bs):
+    class Flaky(BatchStub):
+        def submit_batch(self, staged, multi_of):
+            raise RuntimeError("device batch failed")
+    argv = _dataset(tmp_path, ["a", "b"])
+    a = X.build_parser().parse_args(argv)
+    X.validate_args(a)
+    msgs = []
+    st = X.run_sweep_batched(a, Flaky(), ["a", "b"], batch_size=bs, log=msgs.append)
+    assert st["frame_success"] == 2 and st["face_success"] == 2 and st["multi_success"] == 2
+    assert any("sample by sample" in m for m in msgs)

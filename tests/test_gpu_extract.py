@@ -78,3 +78,37 @@ def test_sweep_matches_oracle_per_sample(tmp_path):
         gm = np.load(root / "multi_CLIP_VIT_LARGE_HUBERT_LARGE_complete" / f"{n}.npy")
         assert gm.shape == (1024,)
         gate(torch.from_numpy(gm)[None], want_multi[None], f"multi/{n}")
+
+
+def test_batched_sweep_files_equal_per_sample_sweep_bit_for_bit(tmp_path):
+    """--batch_size N shares one ViT call and one HuBERT call between N samples; the encoders are batch-invariant bit for
+    bit, so every .npy must equal the file the reference-style per-sample loop writes."""
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import extract as X
+    names = ["clipA", "clipB", "clipC", "clipD", "clipE"]
+    _write_dataset(tmp_path, names)
+    clip = R.build_clip_vision(num_layers=2, seed=1234)
+    hub = R.build_hubert(num_layers=3, feat_extract_norm="layer", seed=1234)
+    model = agb.build_path(clip.state_dict(), hub.state_dict(), R.build_fusion_state(seed=1234), device=DEV, vit_layers=2,
+                           hubert_layers=3)
+    ex = X.MultimodalFeatureExtractor(model.visual_encoder, model.acoustic_encoder, model, device=DEV)
+    trees, stats = [], []
+    for mode, bs in (("single", 1), ("batched", 3)):
+        args = X.build_parser().parse_args([
+            "--dataset", "mer2024", "--video_root", str(tmp_path / "video"), "--face_root", str(tmp_path / "face"),
+            "--audio_root", str(tmp_path / "audio"), "--sample_list", str(tmp_path / "names.txt"),
+            "--save_root", str(tmp_path / mode), "--quiet", "--batch_size", str(bs)])
+        X.validate_args(args)
+        nm = X.read_sample_names(args)
+        st = X.run_sweep(args, ex, nm, log=lambda *_: None) if bs == 1 else \
+            X.run_sweep_batched(args, ex, nm, batch_size=bs, workers=2, log=lambda *_: None)
+        stats.append(st)
+        tree = {}
+        for d, _, files in os.walk(tmp_path / mode):
+            for f in files:
+                tree[os.path.relpath(os.path.join(d, f), tmp_path / mode)] = np.load(os.path.join(d, f))
+        trees.append(tree)
+    assert stats[0] == stats[1] and stats[1]["multi_success"] == 5 and stats[1]["audio_failed"] == 1
+    assert sorted(trees[0]) == sorted(trees[1]) and len(trees[0]) == 4 * 5 + 1
+    for k in trees[0]:
+        assert np.array_equal(trees[0][k], trees[1][k]), k

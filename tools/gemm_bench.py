@@ -41,8 +41,22 @@ for name, M, N, K, act, resid in shapes:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     tf = 2.0 * M * N * K / ms / 1e9
-    res[name] = {"ms": ms, "tflops": tf}
-    print(f"{name:9s} M={M} N={N} K={K}: {ms:.3f} ms  {tf:.0f} TFLOP/s", flush=True)
+    # the library on the same shape (cuBLAS through torch: bare A @ W^T into bf16, no bias / activation / residual)
+    wt = w.t()
+    oc = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        torch.matmul(a, wt, out=oc)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, wt, out=oc)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_lib = e0.elapsed_time(e1) / iters
+    del oc
+    res[name] = {"ms": ms, "tflops": tf, "cublas_ms": ms_lib, "cublas_tflops": 2.0 * M * N * K / ms_lib / 1e9}
+    print(f"{name:9s} M={M} N={N} K={K}: {ms:.3f} ms  {tf:.0f} TFLOP/s   | cuBLAS bare GEMM {ms_lib:.3f} ms "
+          f"{2.0 * M * N * K / ms_lib / 1e9:.0f} TFLOP/s", flush=True)
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 os.makedirs(out, exist_ok=True)
 json.dump(res, open(os.path.join(out, f"gemm_bench_cg{os.environ.get('AGB_GEMM_CTA_GROUP', '2')}.json"), "w"), indent=1)
