@@ -12,6 +12,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// Warp index as a value ptxas can PROVE warp-uniform (a shuffle broadcast), unlike threadIdx.x >> 5.  It matters for every
+// instruction that takes uniform-register operands (tcgen05.mma, tcgen05.commit, cp.async.bulk.tensor, mbarrier addresses):
+// when their operands are computed under control flow that ptxas must assume divergent (`if (threadIdx.x == 32)`), each
+// issue is wrapped in a "waterfall" loop (ELECT + R2UR.BROADCAST per operand + BRA.U.ANY), ~160 clk per tcgen05.mma on
+// B200 - more than a 128x256x16 MMA takes to execute.  Role code therefore runs warp-wide on uniform values and only
+// the issuing instruction itself sits under the elected lane's predicate.
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// one lane of the (converged) warp; the same lane every time it is called with the full mask
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

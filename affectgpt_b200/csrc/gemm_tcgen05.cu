@@ -28,6 +28,7 @@
 // (transformers/models/clip/modeling_clip.py:310-350, models/hubert/modeling_hubert.py:45-231, 262-370).
 #include <cuda.h>
 
+#include <cstring>
 #include <mutex>
 
 #include "agb_internal.h"
@@ -50,16 +51,24 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
 constexpr int kStageBufBytes = 4096;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled (TMA store source)
 
-template <int BN, int CG>
+constexpr int A_POSCONV_SLAB = 3;     // internal variant of A_POSCONV: the A operand is a resident input slab (see below)
+constexpr int kSlabRows = 256;        // 128 output rows + 127 taps of halo (+1), 128 B each
+
+template <int BN, int CG, bool SLAB = false>
 struct Cfg {
-  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kABytes = SLAB ? 0 : BM * BK * 2;        // slab mode: the ring carries W only
   static constexpr int kBBytes = (BN / CG) * BK * 2;            // per CTA: the pair splits W's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSlabBytes = SLAB ? kSlabRows * 128 : 0; // two slabs (this tile's and the next one's)
   static constexpr int kEpiBytes = kNumEpiWarps * kStageBufBytes;
-  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes;
+  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 2 * kSlabBytes;
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
-  static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // slab mode: consecutive taps accumulate into kAcc independent TMEM tiles (summed by the epilogue) - with N = 64 a
+  // tcgen05.mma is 32 clk of tensor work, far less than the latency of a dependent accumulate into the same tile
+  static constexpr int kAcc = SLAB ? 4 : 1;
+  static constexpr int kTmemCols = 2 * BN * kAcc;               // two accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kSlabBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert((kStages * kStageBytes) % 1024 == 0, "slabs / staging buffers need 1024-byte alignment");
 };
 
 struct KParams {
@@ -76,23 +85,28 @@ template <int BN, int MODE, int ACT, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmH, const KParams p) {
-  using C = Cfg<BN, CG>;
+  constexpr bool kSlab = MODE == A_POSCONV_SLAB;
+  constexpr bool kPos = MODE == A_POSCONV || kSlab;
+  using C = Cfg<BN, CG, kSlab>;
   constexpr int S = C::kStages;
-  static_assert(CG == 1 || (MODE != A_POSCONV), "the positional-conv mode runs single-CTA");
+  static_assert(CG == 1 || !kPos, "the positional-conv modes run single-CTA");
   extern __shared__ uint8_t smem_raw[];
   // identical carve-up in both CTAs of a pair: the peer's operands / barriers live at the same offsets
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + S * C::kABytes;
-  uint8_t* smE = smem + S * C::kStageBytes;                       // epilogue staging, 1024-aligned
+  uint8_t* smS = smem + S * C::kStageBytes;                       // slab mode: two input slabs, 1024-aligned
+  uint8_t* smE = smS + 2 * C::kSlabBytes;                         // epilogue staging, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smE + C::kEpiBytes);
   uint64_t* full = bars;            // [S]  TMA -> MMA
   uint64_t* empty = bars + S;       // [S]  MMA -> TMA
   uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
   uint64_t* tempty = tfull + 2;     // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* sfull = tempty + 2;     // [2]  slab mode: TMA -> MMA (input slab resident)
+  uint64_t* sempty = sfull + 2;     // [2]  slab mode: MMA -> TMA (all taps of the tile have read it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
@@ -111,6 +125,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kNumEpiWarps * CG);
+      mbar_init(&sfull[i], 1);
+      mbar_init(&sempty[i], 1);
     }
     fence_mbar_init();
   }
@@ -128,47 +144,67 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
-    // ================================================================ TMA producer (one thread per CTA)
-    if (lane == 0) {
+    // ================================================================ TMA producer
+    // the whole warp runs the loop on warp-uniform values; one elected lane issues (see uniform_warp_id)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      int sit = 0;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++sit) {
         const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
         const int row0 = mt * (BM * CG) + (int)cta_rank * BM;          // this CTA's 128 A rows
         const int wrow0 = nt * BN + (int)cta_rank * (BN / CG);          // this CTA's share of the W tile
+        if constexpr (kSlab) {
+          // rows t - 64 .. t + 191 of sequence mt, the 64 input channels of group nt: every tap's A tile is a
+          // 128-row window of this slab (TMA zero-fills rows outside [0, valid) = the conv's zero padding)
+          const int si = sit & 1;
+          mbar_wait(&sempty[si], ((sit >> 1) & 1) ^ 1u, 6);
+          if (issuer) {
+            mbar_arrive_expect_tx(&sfull[si], C::kSlabBytes);
+            tma_load_3d(smS + si * C::kSlabBytes, &tmA, &sfull[si], nt * 64, -64, mt, kEvictNormal);
+          }
+          __syncwarp();
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 1);
           void* dA = smA + stage * C::kABytes;
           void* dB = smB + stage * C::kBBytes;
-          if constexpr (CG == 2) {
-            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
-            if constexpr (MODE == A_PLAIN) {
-              tma_load_2d_pair(dA, &tmA, &full[stage], kb * BK, row0, kEvictNormal);
+          if (issuer) {
+            if constexpr (CG == 2) {
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::kStageBytes);
+              if constexpr (MODE == A_PLAIN) {
+                tma_load_2d_pair(dA, &tmA, &full[stage], kb * BK, row0, kEvictNormal);
+              } else {
+                tma_load_2d_pair(dA, &tmA, &full[stage], (kb & 15) * BK, row0 + (kb >> 4), kEvictNormal);
+              }
+              tma_load_2d_pair(dB, &tmB, &full[stage], kb * BK, wrow0, kEvictLast);
+              if (!leader) mbar_arrive_remote(&full[stage], 0);
             } else {
-              tma_load_2d_pair(dA, &tmA, &full[stage], (kb & 15) * BK, row0 + (kb >> 4), kEvictNormal);
+              mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
+              if constexpr (MODE == A_PLAIN) {
+                tma_load_2d(dA, &tmA, &full[stage], kb * BK, row0, kEvictNormal);
+              } else if constexpr (MODE == A_CONV3) {
+                // K blocks 0..15: pair row m, cols kb*64; K blocks 16..23: pair row m+1, cols (kb-16)*64
+                tma_load_2d(dA, &tmA, &full[stage], (kb & 15) * BK, row0 + (kb >> 4), kEvictNormal);
+              } else if constexpr (MODE == A_POSCONV) {
+                // mt = sequence, nt = group; tap kb reads rows t + kb - 64 (TMA zero-fills t outside [0, valid))
+                tma_load_3d(dA, &tmA, &full[stage], nt * 64, kb - 64, mt, kEvictNormal);
+              }
+              tma_load_2d(dB, &tmB, &full[stage], kb * BK, wrow0, kEvictLast);
             }
-            tma_load_2d_pair(dB, &tmB, &full[stage], kb * BK, wrow0, kEvictLast);
-            if (!leader) mbar_arrive_remote(&full[stage], 0);
-          } else {
-            mbar_arrive_expect_tx(&full[stage], C::kStageBytes);
-            if constexpr (MODE == A_PLAIN) {
-              tma_load_2d(dA, &tmA, &full[stage], kb * BK, row0, kEvictNormal);
-            } else if constexpr (MODE == A_CONV3) {
-              // K blocks 0..15: pair row m, cols kb*64; K blocks 16..23: pair row m+1, cols (kb-16)*64
-              tma_load_2d(dA, &tmA, &full[stage], (kb & 15) * BK, row0 + (kb >> 4), kEvictNormal);
-            } else {
-              // mt = sequence, nt = group; tap kb reads rows t + kb - 64 (TMA zero-fills t outside [0, valid))
-              tma_load_3d(dA, &tmA, &full[stage], nt * 64, kb - 64, mt, kEvictNormal);
-            }
-            tma_load_2d(dB, &tmB, &full[stage], kb * BK, wrow0, kEvictLast);
           }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (one thread, leader CTA only)
-    if (lane == 0 && leader) {
+    // ================================================================ MMA issuer (leader CTA only)
+    // warp-wide loop on uniform values, one elected lane issues tcgen05.mma / tcgen05.commit (the SAME lane throughout:
+    // a commit tracks the MMAs of the thread that issues it)
+    if (leader) {
+      const bool issuer = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16_f32(BM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -178,27 +214,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1u, 2);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d0 = tmem_base + as * (BN * C::kAcc);
+        uint32_t slab_addr = 0;
+        if constexpr (kSlab) {
+          mbar_wait(&sfull[it & 1], (it >> 1) & 1, 7);
+          slab_addr = smem_u32(smS + (it & 1) * C::kSlabBytes);
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
-          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA + stage * C::kABytes));
-          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + stage * C::kBBytes));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (CG == 2)
-              umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          if constexpr (CG == 2) {
-            umma_commit_pair(&empty[stage], 0x3);                        // smem slot free in both CTAs
-            if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as], 0x3);   // accumulator complete in both CTAs
+          uint64_t da;
+          if constexpr (kSlab) {
+            // tap kb: output row m reads slab row m + kb -> the A tile starts kb rows (kb * 128 B) into the slab.  The
+            // 128B swizzle is a function of the absolute shared-memory address (the slab is 1024-byte aligned), so a
+            // start address that is not 8-row aligned needs nothing else: measured on B200, the descriptor's
+            // matrix-base-offset field must stay 0 here (setting it to (start >> 7) & 7 gives wrong products).
+            da = umma_desc_kmajor_sw128(slab_addr + (uint32_t)kb * 128u);
           } else {
-            umma_commit(&empty[stage]);
-            if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
+            da = umma_desc_kmajor_sw128(smem_u32(smA + stage * C::kABytes));
           }
+          const uint32_t tmem_d = tmem_d0 + (kSlab ? (uint32_t)(kb & (C::kAcc - 1)) * BN : 0u);
+          const int kb_acc = kSlab ? kb / C::kAcc : kb;          // first K block of THIS accumulator overwrites
+          const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + stage * C::kBBytes));
+          if (issuer) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              if constexpr (CG == 2)
+                umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb_acc | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb_acc | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CG == 2) {
+              umma_commit_pair(&empty[stage], 0x3);                        // smem slot free in both CTAs
+              if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as], 0x3);   // accumulator complete in both CTAs
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb == p.num_kb - 1) {
+                umma_commit(&tfull[as]);
+                if constexpr (kSlab) umma_commit(&sempty[it & 1]);
+              }
+            }
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
@@ -226,15 +284,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row_base = MODE == A_POSCONV ? q * 32 : mt * (BM * CG) + (int)cta_rank * BM + q * 32;
+      const int row_base = kPos ? q * 32 : mt * (BM * CG) + (int)cta_rank * BM + q * 32;
       const int col0 = nt * BN + half * HC;
 
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + half * HC);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * (BN * C::kAcc) + half * HC);
 
       uint32_t v[2][32];
       tmem_ld_32x32b_x32(taddr, v[0]);
+      if constexpr (kSlab) {
+        // fold the other accumulators of the tap round-robin into the first one (NCH == 1 here)
+        static_assert(!kSlab || NCH == 1, "slab mode: one 32-column chunk per warp");
+#pragma unroll
+        for (int a2 = 1; a2 < C::kAcc; ++a2) {
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(taddr + a2 * BN, v[1]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[0][j] = __float_as_uint(__uint_as_float(v[0][j]) + __uint_as_float(v[1][j]));
+        }
+      }
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
@@ -280,7 +350,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && cbase < p.N) {
-            if constexpr (MODE == A_POSCONV) {
+            if constexpr (kPos) {
               tma_reduce_add_3d(&tmF, stg, cbase, row_base, mt);
             } else {
               if (p.reduce_f32) tma_reduce_add_2d(&tmF, stg, cbase, row_base); else tma_store_2d(&tmF, stg, cbase, row_base);
@@ -384,7 +454,7 @@ struct Maps {
 template <int BN, int MODE, int ACT, int CG>
 int launch(const Maps& m, const KParams& kp, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, MODE, ACT, CG>;
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, MODE == A_POSCONV_SLAB>;
   static bool configured = false;
   if (!configured) {
     AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -417,6 +487,17 @@ bool use_pairs() {
     v = (e != nullptr && e[0] == '1') ? 0 : 1;
   }
   return v == 1;
+}
+
+// AGB_POSCONV = "tap": one A tile per tap through TMA (first version, L2-bound: 3 MB of operands per 128 x 64 tile);
+// default: resident input slab, every tap's A tile is a row-shifted window of it (1 MB of W per tile).
+int posconv_slab_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("AGB_POSCONV");
+    v = (e && !strcmp(e, "tap")) ? 0 : 1;
+  }
+  return v;
 }
 
 }  // namespace
@@ -480,7 +561,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
                 "gemm: posconv writes resid += gelu(conv) (fp32, row stride 1024)");
     uint64_t dA[3] = {1024, (uint64_t)a.seq_valid, (uint64_t)a.nseq};
     uint64_t sA[2] = {1024 * 2, (uint64_t)a.seq_stride * 1024 * 2};
-    if (int r = make_tmap(&m.a, BF, a.A, 3, dA, sA, 64, BM)) return r;
+    if (int r = make_tmap(&m.a, BF, a.A, 3, dA, sA, 64, posconv_slab_mode() ? kSlabRows : BM)) return r;
     uint64_t sF[2] = {1024 * 4, (uint64_t)a.seq_stride * 1024 * 4};
     if (int r = make_tmap(&m.f, F32, a.out_f32, 3, dA, sF, 32, 32)) return r;   // rows >= seq_valid are clipped
     kp.num_kb = 128;
@@ -505,6 +586,9 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     if (int r = make_tmap(&m.b, BF, a.W, 2, dB, sB, 64, 64)) return r;
     kp.n_tiles = 16;
     AGB_REQUIRE(a.act == ACT_GELU_ERF, "gemm: posconv epilogue is bias + GELU (+ residual)");
+    if (posconv_slab_mode()) {
+      return launch<64, A_POSCONV_SLAB, ACT_GELU_ERF, 1>(m, kp, stream);
+    }
     return launch<64, A_POSCONV, ACT_GELU_ERF, 1>(m, kp, stream);
   }
   if (int r = make_tmap(&m.b, BF, a.W, 2, dB, sB, 64, 256 / cg)) return r;
