@@ -14,15 +14,13 @@
 //     row max and row sum are exchanged through shared memory.
 //   * 257 = 2*128 + 1.  The odd KEY is a 16-row "stray" block: its scores S_C = Q K_C^T (N = 16) are produced one tile
 //     ahead into spare TMEM columns and held in a register, its probability goes through one extra K=16 PV step.
-//     The odd QUERY (row 256 of a 257-token sequence) does not get a tile of its own - a third pass through the serial
-//     chain for one valid row cost a quarter of the kernel.  The two otherwise idle control warps (2 and 3) compute it
-//     on the CUDA cores straight from the K / V tiles that are already in shared memory (257 dot products, exact fp32
-//     softmax, 257 x 64 weighted sum) while the tensor-core chain works on the two full tiles.  (Sequences of 129..256
-//     tokens run the third-tile path below only when seq_valid is not 257: its single valid row is rotated over the
-//     four lane quarters, tile start row 256 - 32*(j%4).)
+//     The odd QUERY is a third tile whose single valid row is rotated over the four lane quarters (tile start row
+//     256 - 32*(j%4)) so that the extra softmax work is spread over the four SM sub-partitions; warps without a
+//     valid row skip the math.  (Computing that row on the CUDA cores in the idle control warps instead, straight from
+//     the K / V tiles in shared memory, was built and measured: 0.435 vs 0.433 ms per ViT layer - no gain, removed.)
 //
 //   warp 0 : TMA producer (K, V single-buffered per head; Q ring of 2)       warp 1 : tcgen05.mma issuer
-//   warp 2 : TMEM allocator; warps 2-3 : stray query row (SIMT)              warps 4-11 : softmax + epilogue
+//   warp 2 : TMEM allocator                                                   warps 4-11 : softmax + epilogue
 //
 // TMEM columns (ViT, NMAIN = 256):  S [0,256)  ->  P_A [0,64) | O [64,128) | P_B [128,192) | P_C [192,200) | S_C(next) [208,224)
 //              (HuBERT, NMAIN = 112): S [0,112) ->  P_A [0,32) | P_B [64,88) ;  O [128,192)
@@ -116,9 +114,7 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t m, uint32_t n, uint32
 
 struct AParams {
   int nseq, seq_stride, seq_valid, qtiles;
-  int simt_row;            // >= 0: this query row of every sequence is computed by warps 2-3 on the CUDA cores
   float scale_log2e;
-  const bf16* qkv;
   bf16* out;
 };
 
@@ -133,10 +129,7 @@ struct Cfg {
   static constexpr int kColO = NMAIN == 256 ? 64 : 128;
   static constexpr int kColPC = 192, kColSC = 208;
   static constexpr int kTmemCols = 256;
-  static constexpr int kOffV = kKVBytes, kOffQ = 2 * kKVBytes, kOffX = kOffQ + 2 * kQBytes;
-  static constexpr int kOffY = kOffX + 2048;                // SIMT stray-query scratch: p[NKROWS] + 8 + 64 floats
-  static constexpr int kYBytes = STRAY ? ((NKROWS + 8 + 64) * 4 + 127) / 128 * 128 : 0;
-  static constexpr int kOffBar = kOffY + kYBytes;
+  static constexpr int kOffV = kKVBytes, kOffQ = 2 * kKVBytes, kOffX = kOffQ + 2 * kQBytes, kOffBar = kOffX + 2048;
   static constexpr int kSmem = kOffBar + 256 + 1024;        // + alignment slack
   static_assert(kKVBytes % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
   static_assert(CA % 32 == 0 && CB % 16 == 0, "column split");
@@ -229,7 +222,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* o_read = bars + 14;    // 8 warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_id(), lane = threadIdx.x & 31;   // provably warp-uniform: see agb_ptx.cuh
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -237,8 +230,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (STRAY) tma_prefetch_desc(&tmStray);
   }
   if (warp == 1 && lane == 0) {
-    const uint32_t kv_readers = (STRAY && p.simt_row >= 0) ? 2u : 1u;     // tensor cores (+ the SIMT stray-query warps)
-    mbar_init(k_full, 1); mbar_init(k_empty, kv_readers); mbar_init(v_full, 1); mbar_init(v_empty, kv_readers);
+    mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1); mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     mbar_init(s_full, 1); mbar_init(sc_full, 1); mbar_init(sc_read, 8);
     mbar_init(pa_ready, 4); mbar_init(pb_ready, 4);
@@ -258,34 +250,47 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    // warp-wide loop on uniform values, one elected lane issues (no per-issue operand waterfall)
+    {
+      const bool issuer = elect_one();
       int t = 0;
       for (int j = 0; j < my_items; ++j) {
         const int item = blockIdx.x + j * gridDim.x;
         const int seq = item >> 4, head = item & 15;
         const int r0 = 32 * (j & 3);
         mbar_wait(k_empty, (j & 1) ^ 1u, 21);
-        mbar_arrive_expect_tx(k_full, C::kKVBytes);
-        tma_load_3d(smK, &tmKV, k_full, 1024 + head * 64, 0, seq, kEvictNormal);
-        if (STRAY) tma_load_3d(smK + NMAIN * 128, &tmStray, k_full, 1024 + head * 64, NMAIN, seq, kEvictNormal);
+        if (issuer) {
+          mbar_arrive_expect_tx(k_full, C::kKVBytes);
+          tma_load_3d(smK, &tmKV, k_full, 1024 + head * 64, 0, seq, kEvictNormal);
+          if (STRAY) tma_load_3d(smK + NMAIN * 128, &tmStray, k_full, 1024 + head * 64, NMAIN, seq, kEvictNormal);
+        }
+        __syncwarp();
         for (int qt = 0; qt < QT; ++qt, ++t) {
           const int qs = t & 1;
           mbar_wait(&q_empty[qs], ((t >> 1) & 1) ^ 1u, 22);
-          mbar_arrive_expect_tx(&q_full[qs], C::kQBytes);
-          tma_load_3d(smQ + qs * C::kQBytes, &tmQ, &q_full[qs], head * 64, qt < 2 ? qt * 128 : 256 - r0, seq,
-                      kEvictFirst);
+          if (issuer) {
+            mbar_arrive_expect_tx(&q_full[qs], C::kQBytes);
+            tma_load_3d(smQ + qs * C::kQBytes, &tmQ, &q_full[qs], head * 64, qt < 2 ? qt * 128 : 256 - r0, seq,
+                        kEvictFirst);
+          }
+          __syncwarp();
           if (qt == 0) {
             mbar_wait(v_empty, (j & 1) ^ 1u, 23);
-            mbar_arrive_expect_tx(v_full, C::kKVBytes);
-            tma_load_3d(smV, &tmKV, v_full, 2048 + head * 64, 0, seq, kEvictNormal);
-            if (STRAY) tma_load_3d(smV + NMAIN * 128, &tmStray, v_full, 2048 + head * 64, NMAIN, seq, kEvictNormal);
+            if (issuer) {
+              mbar_arrive_expect_tx(v_full, C::kKVBytes);
+              tma_load_3d(smV, &tmKV, v_full, 2048 + head * 64, 0, seq, kEvictNormal);
+              if (STRAY) tma_load_3d(smV + NMAIN * 128, &tmStray, v_full, 2048 + head * 64, NMAIN, seq, kEvictNormal);
+            }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0 && T > 0) {
+    // warp-wide loop on uniform values; ONE elected lane (the same throughout) issues every tcgen05.mma / commit
+    if (T > 0) {
+      const bool issuer = elect_one();
       constexpr uint32_t idS = idesc_bf16(128, NMAIN, 0);
       constexpr uint32_t idSC = idesc_bf16(128, 16, 0);
       constexpr uint32_t idO = idesc_bf16(128, 64, 1);
@@ -296,9 +301,12 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint64_t dQ1 = umma_desc_kmajor_sw128(smem_u32(smQ + C::kQBytes));
       auto issue_qk_stray = [&](int t) {
         const uint64_t da = (t & 1) ? dQ1 : dQ0;
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + C::kColSC, da + 2 * k, dKC + 2 * k, idSC, k != 0);
-        umma_commit(sc_full);
+          for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + C::kColSC, da + 2 * k, dKC + 2 * k, idSC, k != 0);
+          umma_commit(sc_full);
+        }
+        __syncwarp();
       };
       if (STRAY) {
         mbar_wait(k_full, 0, 24);
@@ -320,26 +328,35 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc_fence_after();
           {
             const uint64_t da = (t & 1) ? dQ1 : dQ0;
+            if (issuer) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, da + 2 * k, dK + 2 * k, idS, k != 0);
+              for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, da + 2 * k, dK + 2 * k, idS, k != 0);
+              umma_commit(s_full);
+              umma_commit(&q_empty[t & 1]);
+              if (last) umma_commit(k_empty);
+            }
+            __syncwarp();
           }
-          umma_commit(s_full);
-          umma_commit(&q_empty[t & 1]);
-          if (last) umma_commit(k_empty);
           if (first) mbar_wait(v_full, j & 1, 28);
           mbar_wait(pa_ready, ph, 29);
           tc_fence_after();
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < C::CA / 16; ++k)
-            umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPA + 8 * k, dV + 128 * k, idO, k != 0);
+            for (int k = 0; k < C::CA / 16; ++k)
+              umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPA + 8 * k, dV + 128 * k, idO, k != 0);
+          }
+          __syncwarp();
           mbar_wait(pb_ready, ph, 30);
           tc_fence_after();
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < C::CB / 16; ++k)
-            umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPB + 8 * k, dV + 128 * (C::CA / 16 + k), idO, 1u);
-          if (STRAY) umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPC, dV + 128 * (NMAIN / 16), idO, 1u);
-          umma_commit(o_full);
-          if (last) umma_commit(v_empty);
+            for (int k = 0; k < C::CB / 16; ++k)
+              umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPB + 8 * k, dV + 128 * (C::CA / 16 + k), idO, 1u);
+            if (STRAY) umma_bf16_ts(tmem_base + C::kColO, tmem_base + C::kColPC, dV + 128 * (NMAIN / 16), idO, 1u);
+            umma_commit(o_full);
+            if (last) umma_commit(v_empty);
+          }
+          __syncwarp();
           if (STRAY && t + 1 < T) {                               // stray-key scores of the next tile, one tile ahead
             if (last) mbar_wait(k_full, (j + 1) & 1, 24);
             mbar_wait(&q_full[(t + 1) & 1], ((t + 1) >> 1) & 1, 25);
@@ -348,91 +365,6 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
       }
-    }
-  } else if (STRAY && p.simt_row >= 0 && (warp == 2 || warp == 3)) {
-    // ================================================================ stray query row on the CUDA cores (64 threads)
-    // K and V rows sit in smem as TMA wrote them: row r at r * 128 B, 16-byte chunk c stored at chunk c ^ (r & 7).
-    float* sp = reinterpret_cast<float*>(smem + C::kOffY);     // [NKROWS] probabilities (unnormalised)
-    float* sx = sp + C::NKROWS;                                // [8] cross-warp max / sum
-    float* so = sx + 8;                                        // [64] warp 3's partial output
-    const int w = warp - 2, tid = w * 32 + lane;
-    const int valid = p.seq_valid;
-    constexpr int KPT = (C::NKROWS + 63) / 64;                 // keys per thread
-    for (int j = 0; j < my_items; ++j) {
-      const int item = blockIdx.x + j * gridDim.x;
-      const int seq = item >> 4, head = item & 15;
-      uint4 q[8];                                              // the query row, 64 bf16 (kept packed: 32 registers)
-      {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + ((long long)seq * p.seq_stride + p.simt_row) * 3072 + head * 64);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = __ldg(qp + c);
-      }
-      mbar_wait(k_full, j & 1, 40);
-      float sc[KPT];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < KPT; ++i) {
-        const int key = tid + 64 * i;
-        float acc = -INFINITY;
-        if (key < valid) {
-          const uint8_t* row = smK + key * 128;
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint4 u = *reinterpret_cast<const uint4*>(row + ((c ^ (key & 7)) << 4));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-            const __nv_bfloat162* g = reinterpret_cast<const __nv_bfloat162*>(&q[c]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]), qq = __bfloat1622float2(g[e]);
-              a0 = fmaf(qq.x, f.x, a0);
-              a1 = fmaf(qq.y, f.y, a1);
-            }
-          }
-          acc = (a0 + a1) * p.scale_log2e;                     // log2 domain, like the main path
-        }
-        sc[i] = acc;
-        mx = fmaxf(mx, acc);
-      }
-      mx = warp_max(mx);
-      if (lane == 0) sx[w] = mx;
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      mx = fmaxf(sx[0], sx[1]);
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < KPT; ++i) {
-        const int key = tid + 64 * i;
-        if (key < C::NKROWS) {
-          const float e = key < valid ? ex2_approx(sc[i] - mx) : 0.f;
-          sp[key] = e;
-          sum += e;
-        }
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) sx[2 + w] = sum;
-      mbar_wait(v_full, j & 1, 41);
-      asm volatile("bar.sync 2, 64;" ::: "memory");
-      const float inv = 1.0f / (sx[2] + sx[3]);
-      // warp w takes the keys of its parity, lane l the head channels 2l, 2l+1
-      float o0 = 0.f, o1 = 0.f;
-      const uint32_t cofs = (uint32_t)(lane & 3) * 4u, chunk = (uint32_t)lane >> 2;
-#pragma unroll 4
-      for (int key = w; key < valid; key += 2) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(smV + key * 128 + (((chunk ^ (key & 7)) << 4) + cofs)));
-        const float pk = sp[key];
-        o0 = fmaf(pk, f.x, o0);
-        o1 = fmaf(pk, f.y, o1);
-      }
-      if (w == 1) { so[2 * lane] = o0; so[2 * lane + 1] = o1; }
-      asm volatile("bar.sync 2, 64;" ::: "memory");               // every K / V / sp read of this head is done
-      if (w == 0) {
-        o0 = (o0 + so[2 * lane]) * inv;
-        o1 = (o1 + so[2 * lane + 1]) * inv;
-        bf16* dst = p.out + ((long long)seq * p.seq_stride + p.simt_row) * 1024 + head * 64;
-        reinterpret_cast<__nv_bfloat162*>(dst)[lane] = __floats2bfloat162_rn(o0, o1);
-        if (lane == 0) { mbar_arrive(k_empty); mbar_arrive(v_empty); }
-      }
-      asm volatile("bar.sync 2, 64;" ::: "memory");               // so[] / sx[] are free for the next head
     }
   } else if (warp >= 4) {
     // ================================================================ softmax + epilogue (8 warps)
@@ -593,14 +525,8 @@ int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_val
   if (int r = make_tmap_generic(&tst, 0, qkv, 3, dims, strides, 64, 16)) return r;
   AParams p{};
   p.nseq = nseq; p.seq_stride = seq_stride; p.seq_valid = seq_valid;
-  // 257 tokens (ViT): two full query tiles on the tensor cores, row 256 on the CUDA cores (warps 2-3)
-  static int simt = -1;
-  if (simt < 0) { const char* e = getenv("AGB_ATTN_SIMT_ROW"); simt = (e && e[0] == '0') ? 0 : 1; }   // A/B switch
-  const bool simt_row = STRAY && simt == 1 && seq_valid == NMAIN + 1;
-  p.qtiles = simt_row ? NMAIN / 128 : (seq_valid + 127) / 128;
-  p.simt_row = simt_row ? NMAIN : -1;
+  p.qtiles = (seq_valid + 127) / 128;
   p.scale_log2e = scale * 1.4426950408889634f;
-  p.qkv = qkv;
   p.out = out;
   const int items = nseq * 16;
   const int resident = sm_count() * 2;

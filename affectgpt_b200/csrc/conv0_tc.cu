@@ -75,7 +75,7 @@ conv0_tc_kernel(const float* __restrict__ wav, const float* __restrict__ stats, 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_id(), lane = tid & 31;
   const long long seg = blockIdx.y;
   const int t0 = blockIdx.x * kTileRows;
 
@@ -135,16 +135,19 @@ conv0_tc_kernel(const float* __restrict__ wav, const float* __restrict__ stats, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp == 1 && lane == 0) {
+  if (warp == 1) {                     // operands computed warp-wide (uniform registers), one elected lane issues
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 256);
     const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA));
     const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smW));
+    if (elect_one()) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16_ss(tmem_base + h * 256, da + 2 * k, db + h * ((256 * 128) >> 4) + 2 * k, idesc, k != 0);
-    umma_commit(bar);
+        for (int k = 0; k < 2; ++k)
+          umma_bf16_ss(tmem_base + h * 256, da + 2 * k, db + h * ((256 * 128) >> 4) + 2 * k, idesc, k != 0);
+      umma_commit(bar);
+    }
+    __syncwarp();
   }
   mbar_wait(bar, 0, 41);
   tc_fence_after();
