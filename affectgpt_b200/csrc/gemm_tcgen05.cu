@@ -61,14 +61,17 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSlabBytes = SLAB ? kSlabRows * 128 : 0; // two slabs (this tile's and the next one's)
   static constexpr int kEpiBytes = kNumEpiWarps * kStageBufBytes;
-  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 2 * kSlabBytes;
-  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kBarBytes = 512;                         // 2 * kStages + 8 mbarriers + the TMEM slot
+  static constexpr int kBudget = 232448 - 1024 - kBarBytes - kEpiBytes - 2 * kSlabBytes;
+  static constexpr int kMaxStages = SLAB ? 14 : 8;              // slab mode: 8 KB stages, deep ring hides the L2 latency
+  static constexpr int kStages = kBudget / kStageBytes > kMaxStages ? kMaxStages : kBudget / kStageBytes;
   // slab mode: consecutive taps accumulate into kAcc independent TMEM tiles (summed by the epilogue) - with N = 64 a
   // tcgen05.mma is 32 clk of tensor work, far less than the latency of a dependent accumulate into the same tile
   static constexpr int kAcc = SLAB ? 4 : 1;
   static constexpr int kTmemCols = 2 * BN * kAcc;               // two accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kSlabBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kSlabBytes + kEpiBytes + 1024 /*align*/ + kBarBytes;
   static_assert((kStages * kStageBytes) % 1024 == 0, "slabs / staging buffers need 1024-byte alignment");
+  static_assert((2 * kStages + 8) * 8 + 16 <= kBarBytes, "barrier region");
 };
 
 struct KParams {
@@ -489,13 +492,16 @@ bool use_pairs() {
   return v == 1;
 }
 
-// AGB_POSCONV = "tap": one A tile per tap through TMA (first version, L2-bound: 3 MB of operands per 128 x 64 tile);
-// default: resident input slab, every tap's A tile is a row-shifted window of it (1 MB of W per tile).
+// Positional conv A operand.  Default "tap": one TMA A tile per tap (3 MB of operands per 128 x 64 tile, all L2 hits).
+// AGB_POSCONV=slab: resident input slab, every tap's A tile is a row-shifted window of it (1 MB of W per tile) with four
+// round-robin accumulators.  Measured on B200 once the issue waterfall was gone: tap 1.88 ms, slab 2.02 ms per 512
+// sequences (the unaligned windows read shared memory less efficiently than the L2 serves whole tiles), so the slab
+// variant stays an experiment - it is the starting point for sharing W between sequences.
 int posconv_slab_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("AGB_POSCONV");
-    v = (e && !strcmp(e, "tap")) ? 0 : 1;
+    v = (e && !strcmp(e, "slab")) ? 1 : 0;
   }
   return v;
 }
