@@ -10,33 +10,47 @@ namespace agb {
 
 namespace {
 
-// out[m, n] = sum_k in[m,k] * W[n,k] + bias[n].  Block: 64 (n) x 16 (m) outputs, K tiles of 32 in smem.
-constexpr int LT_N = 64, LT_M = 16, LT_K = 32;
+// out[m, n] = sum_k in[m,k] * W[n,k] + bias[n].  Block: 32 (n) x 64 (m) outputs - a whole batch of clips per block, so W
+// is read once - K tiles of 32 in smem, the next tile prefetched into registers while this one is multiplied.  One fp32
+// accumulator per output, k ascending (the order of a plain dot product).
+constexpr int LT_N = 32, LT_M = 64, LT_K = 32;
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, long long ld_in,
                                                     const float* __restrict__ W, const float* __restrict__ bias,
                                                     float* __restrict__ out, long long ld_out, int M, int N, int K) {
   __shared__ float sW[LT_N][LT_K + 1];
   __shared__ float sI[LT_M][LT_K + 1];
   const int n0 = blockIdx.x * LT_N, m0 = blockIdx.y * LT_M;
-  const int tn = threadIdx.x & 63, tm = threadIdx.x >> 6;  // thread -> n = tn, m = tm*4 .. tm*4+3
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tn = threadIdx.x & 31, tm = threadIdx.x >> 5;  // thread -> n = tn, m = tm*8 .. tm*8+7 (a warp shares its rows)
+  const int lc = threadIdx.x & 31, lr = threadIdx.x >> 5;  // loader: column lc, rows lr + 8*i
+  float acc[8], pw[4], pi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  auto fetch = [&](int k0) {
+    const int k = k0 + lc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + lr + 8 * i;
+      pw[i] = (n < N && k < K) ? __ldg(W + (long long)n * K + k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + lr + 8 * i;
+      pi[i] = (m < M && k < K) ? __ldg(in + (long long)m * ld_in + k) : 0.f;
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < K; k0 += LT_K) {
-    for (int i = threadIdx.x; i < LT_N * LT_K; i += 256) {
-      const int r = i / LT_K, c = i % LT_K;
-      const int n = n0 + r, k = k0 + c;
-      sW[r][c] = (n < N && k < K) ? W[(long long)n * K + k] : 0.f;
-    }
-    for (int i = threadIdx.x; i < LT_M * LT_K; i += 256) {
-      const int r = i / LT_K, c = i % LT_K;
-      const int m = m0 + r, k = k0 + c;
-      sI[r][c] = (m < M && k < K) ? in[(long long)m * ld_in + k] : 0.f;
-    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sW[lr + 8 * i][lc] = pw[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sI[lr + 8 * i][lc] = pi[i];
     __syncthreads();
+    if (k0 + LT_K < K) fetch(k0 + LT_K);
 #pragma unroll
     for (int k = 0; k < LT_K; ++k) {
       const float w = sW[tn][k];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(sI[tm * 4 + j][k], w, acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(sI[tm * 8 + j][k], w, acc[j]);
     }
     __syncthreads();
   }
@@ -44,8 +58,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
   if (n < N) {
     const float b = bias != nullptr ? bias[n] : 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = m0 + tm * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int m = m0 + tm * 8 + j;
       if (m < M) out[(long long)m * ld_out + n] = acc[j] + b;
     }
   }
