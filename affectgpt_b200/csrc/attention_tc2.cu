@@ -14,10 +14,14 @@
 //     row max and row sum are exchanged through shared memory.
 //   * 257 = 2*128 + 1.  The odd KEY is a 16-row "stray" block: its scores S_C = Q K_C^T (N = 16) are produced one tile
 //     ahead into spare TMEM columns and held in a register, its probability goes through one extra K=16 PV step.
-//     The odd QUERY is a third tile whose single valid row is rotated over the four lane quarters (tile start row
-//     256 - 32*(j%4)) so that the extra softmax work is spread over the four SM sub-partitions; warps without a
-//     valid row skip the math.  (Computing that row on the CUDA cores in the idle control warps instead, straight from
-//     the K / V tiles in shared memory, was built and measured: 0.435 vs 0.433 ms per ViT layer - no gain, removed.)
+//     The odd QUERY (row 256 of a 257-token sequence) gets no tile of its own.  A clock64 trace (AGB_ATTN_TRACE=1) showed
+//     a third tile with one valid row costs as much as a full one (6.9 K of an item's 20 K clk): the one warp that owns
+//     the row still walks all 272 columns at single-warp latency.  Instead the 256 softmax threads compute that row on
+//     the CUDA cores from the K / V tiles already in shared memory, inside the two windows where they would otherwise
+//     wait for the tensor cores: one key per thread (64-wide dot product) + block softmax while Q.K^T of the first tile
+//     runs, and the 257 x 64 weighted sum of V while its P.V runs.  (A first attempt that gave the whole row to the two
+//     idle control warps was correct but no faster: 64 threads were too slow and held K / V back.)
+//     Sequences of 129..256 tokens have no odd query; other odd lengths would use the rotating third tile below.
 //
 //   warp 0 : TMA producer (K, V single-buffered per head; Q ring of 2)       warp 1 : tcgen05.mma issuer
 //   warp 2 : TMEM allocator                                                   warps 4-11 : softmax + epilogue
@@ -33,6 +37,9 @@
 // Replaces CLIPAttention.forward (HF modeling_clip.py:262-332, scale 1/8, fp32 softmax) and
 // HubertAttention.forward (HF modeling_hubert.py:262-370).
 #include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "agb_internal.h"
 #include "agb_ptx.cuh"
@@ -114,8 +121,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t m, uint32_t n, uint32
 
 struct AParams {
   int nseq, seq_stride, seq_valid, qtiles;
+  int stray_q;             // 1: query row NMAIN of every sequence is computed by the softmax warps on the CUDA cores
   float scale_log2e;
+  const bf16* qkv;
   bf16* out;
+  long long* trace;        // AGB_ATTN_TRACE=1: clock64 stamps of the first 64 tiles of CTA 0 (tools/attn_trace.py), else null
 };
 
 template <int NMAIN, bool STRAY>
@@ -129,7 +139,10 @@ struct Cfg {
   static constexpr int kColO = NMAIN == 256 ? 64 : 128;
   static constexpr int kColPC = 192, kColSC = 208;
   static constexpr int kTmemCols = 256;
-  static constexpr int kOffV = kKVBytes, kOffQ = 2 * kKVBytes, kOffX = kOffQ + 2 * kQBytes, kOffBar = kOffX + 2048;
+  static constexpr int kOffV = kKVBytes, kOffQ = 2 * kKVBytes, kOffX = kOffQ + 2 * kQBytes;
+  static constexpr int kOffY = kOffX + 2048;                // odd query row: p[NKROWS] | 16 reduction slots | q[64] | 8 x 64 partial outputs
+  static constexpr int kYBytes = STRAY ? ((NKROWS + 16 + 64 + 512) * 4 + 127) / 128 * 128 : 0;
+  static constexpr int kOffBar = kOffY + kYBytes;
   static constexpr int kSmem = kOffBar + 256 + 1024;        // + alignment slack
   static_assert(kKVBytes % 1024 == 0, "swizzle atoms need 1024-byte aligned tiles");
   static_assert(CA % 32 == 0 && CB % 16 == 0, "column split");
@@ -326,6 +339,8 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (t > 0) mbar_wait(o_read, ph ^ 1u, 26);            // epilogue of tile t-1 has drained TMEM
           if (STRAY) mbar_wait(sc_read, ph, 27);                // S_C(t) is in registers
           tc_fence_after();
+          const bool tr = p.trace != nullptr && blockIdx.x == 0 && t < 64 && issuer;
+          if (tr) p.trace[t * 16 + 0] = clock64();
           {
             const uint64_t da = (t & 1) ? dQ1 : dQ0;
             if (issuer) {
@@ -340,6 +355,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (first) mbar_wait(v_full, j & 1, 28);
           mbar_wait(pa_ready, ph, 29);
           tc_fence_after();
+          if (tr) p.trace[t * 16 + 1] = clock64();
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < C::CA / 16; ++k)
@@ -348,6 +364,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           __syncwarp();
           mbar_wait(pb_ready, ph, 30);
           tc_fence_after();
+          if (tr) p.trace[t * 16 + 2] = clock64();
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < C::CB / 16; ++k)
@@ -357,6 +374,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (last) umma_commit(v_empty);
           }
           __syncwarp();
+          if (tr) p.trace[t * 16 + 3] = clock64();
           if (STRAY && t + 1 < T) {                               // stray-key scores of the next tile, one tile ahead
             if (last) mbar_wait(k_full, (j + 1) & 1, 24);
             mbar_wait(&q_full[(t + 1) & 1], ((t + 1) >> 1) & 1, 25);
@@ -385,11 +403,61 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(sc_read);
     }
+    const bool stray_q = STRAY && p.stray_q != 0;
+    float* sp = reinterpret_cast<float*>(smem + C::kOffY);   // unnormalised probabilities of the odd query row
+    float* sred = sp + C::NKROWS;                             // [0,8) warp maxima, [8,16) warp sums
+    float* sq = sred + 16;                                    // [64] the odd query row, fp32, pre-scaled (log2 domain)
+    float* so = sq + 64;                                      // [8 key eighths][64 channels]
+    const int tid2 = (warp - 4) * 32 + lane;                  // 0..255 over the softmax warps
+    // the odd query row's element for thread tid2 < 64, fetched one item ahead (a global-load latency per item otherwise)
+    auto load_q = [&](int jj) -> float {
+      if (!stray_q || tid2 >= 64 || jj >= my_items) return 0.f;
+      const int it2 = blockIdx.x + jj * gridDim.x;
+      return __bfloat162float(p.qkv[((long long)(it2 >> 4) * p.seq_stride + NMAIN) * 3072 + (it2 & 15) * 64 + tid2]);
+    };
+    float q_next = load_q(0);
     int t = 0;
     for (int j = 0; j < my_items; ++j) {
       const int item = blockIdx.x + j * gridDim.x;
       const int seq = item >> 4, head = item & 15;
       const int r0 = 32 * (j & 3);
+      if (stray_q) {
+        // ---- odd query row, part 1 (while Q.K^T of the first tile runs): thread = key, scores in the log2 domain,
+        // block max / sum, probabilities to shared memory.  K rows as TMA wrote them: chunk c of row r at c ^ (r & 7).
+        if (tid2 < 64) sq[tid2] = q_next * sc;
+        q_next = load_q(j + 1);
+        mbar_wait(k_full, j & 1, 35);
+        softmax_bar_sync();
+        float s0, s1;
+        {
+          const uint8_t* row = smK + tid2 * 128;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 u = *reinterpret_cast<const uint4*>(row + ((c ^ (tid2 & 7)) << 4));
+            const float4 qa = *reinterpret_cast<const float4*>(sq + c * 8), qb = *reinterpret_cast<const float4*>(sq + c * 8 + 4);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]),
+                         f3 = __bfloat1622float2(h[3]);
+            a0 = fmaf(qa.x, f0.x, a0); a1 = fmaf(qa.y, f0.y, a1); a2 = fmaf(qa.z, f1.x, a2); a3 = fmaf(qa.w, f1.y, a3);
+            a0 = fmaf(qb.x, f2.x, a0); a1 = fmaf(qb.y, f2.y, a1); a2 = fmaf(qb.z, f3.x, a2); a3 = fmaf(qb.w, f3.y, a3);
+          }
+          s0 = (a0 + a1) + (a2 + a3);
+          // key 256 = row 0 of the stray block (chunk order unswizzled): every warp forms the dot product with a shuffle sum
+          const float2 kf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(smK + NMAIN * 128)[lane]);
+          s1 = warp_sum(fmaf(sq[2 * lane], kf.x, sq[2 * lane + 1] * kf.y));
+          if (tid2 != 0) s1 = -INFINITY;                                   // counted once, by thread 0
+        }
+        float mx = warp_max(fmaxf(s0, s1));
+        if (lane == 0) sred[warp - 4] = mx;
+        softmax_bar_sync();
+        mx = fmaxf(fmaxf(fmaxf(sred[0], sred[1]), fmaxf(sred[2], sred[3])), fmaxf(fmaxf(sred[4], sred[5]), fmaxf(sred[6], sred[7])));
+        const float p0 = ex2_approx(s0 - mx), p1 = tid2 == 0 ? ex2_approx(s1 - mx) : 0.f;
+        sp[tid2] = p0;
+        if (tid2 == 0) sp[NMAIN] = p1;
+        const float ls = warp_sum(p0 + p1);
+        if (lane == 0) sred[8 + warp - 4] = ls;      // sp / sred[8..] are read in part 2, after the barrier of tile 0's pass 1
+      }
       for (int qt = 0; qt < QT; ++qt, ++t) {
         const uint32_t ph = t & 1;
         const int grow = (qt < 2 ? qt * 128 : 256 - r0) + row_in_tile;
@@ -397,6 +465,8 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const bool active = __any_sync(0xffffffffu, mine);
         mbar_wait(s_full, ph, 32);
         tc_fence_after();
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && t < 64 && warp == 4 && lane == 0;
+        if (tr) p.trace[t * 16 + 8] = clock64();
         // ---------------- pass 1: row max over this group's key columns
         float m = -INFINITY;
         if (active) {
@@ -411,7 +481,9 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         xm[grp * 128 + row_in_tile] = m;
+        if (tr) p.trace[t * 16 + 9] = clock64();
         softmax_bar_sync();
+        if (tr) p.trace[t * 16 + 10] = clock64();
         m = fmaxf(m, xm[(grp ^ 1) * 128 + row_in_tile]);
         const float mo = m * sc;
         // ---------------- pass 2: exponentials, row sum, P (bf16) written over the consumed S columns
@@ -442,6 +514,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
+        if (tr) p.trace[t * 16 + 11] = clock64();
         if (lane == 0) mbar_arrive(grp == 0 ? pa_ready : pb_ready);
         xl[grp * 128 + row_in_tile] = l;
         if (STRAY && t + 1 < T) {                     // pick up the next tile's stray-key score while P.V runs
@@ -453,9 +526,39 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(sc_read);
         }
+        if (stray_q && qt == 0) {
+          // ---- odd query row, part 2 (while P.V of this tile runs): thread = (channel, key quarter)
+          mbar_wait(v_full, j & 1, 36);
+          const int part = warp - 4;                                       // 32 keys per warp, lane = channel pair
+          const uint32_t cofs = (uint32_t)(lane & 3) * 4u, chunk = (uint32_t)lane >> 2;
+          float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll 8
+          for (int key = part * 32; key < part * 32 + 32; key += 2) {
+            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(smV + key * 128 + (((chunk ^ (key & 7)) << 4) + cofs)));
+            const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(smV + (key + 1) * 128 + (((chunk ^ ((key + 1) & 7)) << 4) + cofs)));
+            const float pa = sp[key], pb = sp[key + 1];
+            o0 = fmaf(pa, fa.x, o0); o1 = fmaf(pa, fa.y, o1);
+            o2 = fmaf(pb, fb.x, o2); o3 = fmaf(pb, fb.y, o3);
+          }
+          if (part == 7) {
+            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(smV + NMAIN * 128 + ((chunk << 4) + cofs)));
+            o0 = fmaf(sp[NMAIN], fa.x, o0); o1 = fmaf(sp[NMAIN], fa.y, o1);
+          }
+          so[part * 64 + 2 * lane] = o0 + o2;
+          so[part * 64 + 2 * lane + 1] = o1 + o3;
+          softmax_bar_sync();
+          if (tid2 < 64) {
+            const float l_stray = ((sred[8] + sred[9]) + (sred[10] + sred[11])) + ((sred[12] + sred[13]) + (sred[14] + sred[15]));
+            float o = 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) o += so[g * 64 + tid2];
+            p.out[((long long)seq * p.seq_stride + NMAIN) * 1024 + head * 64 + tid2] = __float2bfloat16_rn(o / l_stray);
+          }
+        }
         // ---------------- epilogue: O / l -> bf16 -> global; each group writes 32 of the 64 head channels
         mbar_wait(o_full, ph, 34);
         tc_fence_after();
+        if (tr) p.trace[t * 16 + 12] = clock64();
         softmax_bar_sync();
         l += xl[(grp ^ 1) * 128 + row_in_tile];
         if (active) {
@@ -483,6 +586,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) mbar_arrive(o_read);
         }
+        if (tr) p.trace[t * 16 + 13] = clock64();
         sc_cur = sc_next;
       }
     }
@@ -525,14 +629,38 @@ int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_val
   if (int r = make_tmap_generic(&tst, 0, qkv, 3, dims, strides, 64, 16)) return r;
   AParams p{};
   p.nseq = nseq; p.seq_stride = seq_stride; p.seq_valid = seq_valid;
-  p.qtiles = (seq_valid + 127) / 128;
+  // 257 tokens (ViT): two full query tiles on the tensor cores, row 256 on the CUDA cores inside the softmax warps' idle windows
+  static int stray_mode = -1;
+  if (stray_mode < 0) { const char* e = getenv("AGB_ATTN_STRAY_TILE"); stray_mode = (e && e[0] == '1') ? 0 : 1; }   // A/B: 1 = third tile
+  p.stray_q = (STRAY && stray_mode == 1 && seq_valid == NMAIN + 1) ? 1 : 0;
+  p.qtiles = p.stray_q ? NMAIN / 128 : (seq_valid + 127) / 128;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.qkv = qkv;
   p.out = out;
+  static long long* trace_buf = nullptr;
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* e = getenv("AGB_ATTN_TRACE"); trace_on = (e && e[0] == '1') ? 1 : 0; }
+  if (trace_on && trace_buf == nullptr) AGB_CHECK_CUDA(cudaMalloc(&trace_buf, 64 * 16 * sizeof(long long)));
+  p.trace = trace_on ? trace_buf : nullptr;
   const int items = nseq * 16;
   const int resident = sm_count() * 2;
   const int grid = items < resident ? items : resident;
   kern<<<grid, kThreads, C::kSmem, s>>>(tq, tkv, tst, p);
   AGB_CHECK_LAUNCH();
+  if (trace_on) {                                       // diagnostic mode only: synchronous dump of the stamps
+    static long long host[64 * 16];
+    AGB_CHECK_CUDA(cudaStreamSynchronize(s));
+    AGB_CHECK_CUDA(cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    printf("attn-trace NMAIN=%d qtiles=%d: tile | MMA: qk_issue pa_ready pb_ready pv_issued | softmax: s_full pass1 bar pass2 o_full done (clk from tile 8's qk_issue)\n", NMAIN, p.qtiles);
+    const long long t00 = host[8 * 16];
+    for (int t = 8; t < 20; ++t) {
+      printf("attn-trace %2d |", t);
+      for (int k : {0, 1, 2, 3}) printf(" %7lld", host[t * 16 + k] - t00);
+      printf(" |");
+      for (int k : {8, 9, 10, 11, 12, 13}) printf(" %7lld", host[t * 16 + k] - t00);
+      printf("\n");
+    }
+  }
   return 0;
 }
 
