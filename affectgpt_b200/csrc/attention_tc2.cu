@@ -163,20 +163,8 @@ __device__ __forceinline__ float chunk_max(uint32_t taddr, int key0, int valid, 
   }
   return m;
 }
-// exp2 on the FMA pipe for x <= ~0 (Cody-Waite: x = j + r, |r| <= 0.5, 2^r by a cubic, 2^j by an exponent add); relative
-// error 8e-5, far inside the bf16 rounding of P.  Used for a quarter of the columns when the exp pass is MUFU-bound.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;                      // 1.5 * 2^23: the low mantissa bits of t hold round(x)
-  const float r = x - (t - 12582912.f);
-  float pl = fmaf(r, 0.05508868396282196f, 0.24260404706001282f);
-  pl = fmaf(pl, r, 0.6932762265205383f);
-  pl = fmaf(pl, r, 0.9999289512634277f);
-  return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(t) << 23));
-}
-
 // ---- softmax pass 2: p = exp2(s*sc - mo), row-sum, bf16 pairs stored at p_addr (W/2 columns)
-template <int W, bool POLY>
+template <int W>
 __device__ __forceinline__ float chunk_exp(uint32_t s_addr, uint32_t p_addr, int key0, int valid, float sc, float mo,
                                            float l) {
   uint32_t v[W];
@@ -196,9 +184,8 @@ __device__ __forceinline__ float chunk_exp(uint32_t s_addr, uint32_t p_addr, int
       asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(x2) : "l"(s2), "l"(sc2), "l"(mo2));
       float x0, x1;
       asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
-      const bool on_fma = POLY && ((j >> 1) & 3) == 3;             // every fourth pair leaves the MUFU alone
-      const float p0 = on_fma ? ex2_poly(x0) : ex2_approx(x0);
-      const float p1 = on_fma ? ex2_poly(x1) : ex2_approx(x1);
+      const float p0 = ex2_approx(x0);
+      const float p1 = ex2_approx(x1);
       asm("mov.b64 %0, {%1, %2};" : "=l"(p2) : "f"(p0), "f"(p1));
       asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc) : "l"(acc), "l"(p2));
       v[j >> 1] = pack_bf16x2(p0, p1);
@@ -220,7 +207,7 @@ __device__ __forceinline__ float chunk_exp(uint32_t s_addr, uint32_t p_addr, int
   return l + l1;
 }
 
-template <int NMAIN, bool STRAY, bool POLY>
+template <int NMAIN, bool STRAY>
 __global__ void __launch_bounds__(kThreads, 2)
 mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                const __grid_constant__ CUtensorMap tmStray, const AParams p) {
@@ -505,13 +492,13 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (grp == 0) {
 #pragma unroll
             for (int c = 0; c < C::CA / 32; ++c)
-              l = chunk_exp<32, POLY>(lane_base + c * 32, lane_base + C::kColPA + c * 16, c * 32, valid, sc, mo, l);
+              l = chunk_exp<32>(lane_base + c * 32, lane_base + C::kColPA + c * 16, c * 32, valid, sc, mo, l);
           } else {
 #pragma unroll
             for (int c = 0; c < C::CB / 32; ++c)
-              l = chunk_exp<32, POLY>(lane_base + C::CA + c * 32, lane_base + C::kColPB + c * 16, C::CA + c * 32, valid, sc, mo, l);
+              l = chunk_exp<32>(lane_base + C::CA + c * 32, lane_base + C::kColPB + c * 16, C::CA + c * 32, valid, sc, mo, l);
             if (C::CB % 32)
-              l = chunk_exp<16, POLY>(lane_base + C::CA + (C::CB / 32) * 32, lane_base + C::kColPB + (C::CB / 32) * 16,
+              l = chunk_exp<16>(lane_base + C::CA + (C::CB / 32) * 32, lane_base + C::kColPB + (C::CB / 32) * 16,
                                 C::CA + (C::CB / 32) * 32, valid, sc, mo, l);
             if (STRAY) {
               uint32_t pc[8];
@@ -624,10 +611,10 @@ int sm_count() {
   return n;
 }
 
-template <int NMAIN, bool STRAY, bool POLY>
+template <int NMAIN, bool STRAY>
 int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s) {
   using C = Cfg<NMAIN, STRAY>;
-  auto kern = mha_tc2_kernel<NMAIN, STRAY, POLY>;
+  auto kern = mha_tc2_kernel<NMAIN, STRAY>;
   static bool configured = false;
   if (!configured) {
     AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
@@ -681,14 +668,8 @@ int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_val
 
 // returns -1 when the shape is not covered by an instantiation (caller falls back)
 int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s) {
-  static int poly = -1;     // AGB_ATTN_POLY=1: a quarter of the exponentials on the FMA pipe (A/B switch)
-  if (poly < 0) { const char* e = getenv("AGB_ATTN_POLY"); poly = (e && e[0] == '1') ? 1 : 0; }
-  if (seq_valid <= 112)
-    return poly ? launch_tc2<112, false, true>(qkv, out, nseq, seq_stride, seq_valid, scale, s)
-                : launch_tc2<112, false, false>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
-  if (seq_valid > 128 && seq_valid <= 257)
-    return poly ? launch_tc2<256, true, true>(qkv, out, nseq, seq_stride, seq_valid, scale, s)
-                : launch_tc2<256, true, false>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+  if (seq_valid <= 112) return launch_tc2<112, false>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+  if (seq_valid > 128 && seq_valid <= 257) return launch_tc2<256, true>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   return -1;
 }
 
