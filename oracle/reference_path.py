@@ -13,8 +13,9 @@ the reference's own thin code around them:
 * ``encode_multi_attention``  <- A/my_affectgpt/models/affectgpt.py:883-908
 * mean-fusion variants        <- A/my_affectgpt/models/affectgpt.py:601-608, 766-773
 
-Parity status: unpinned at the HF boundary (no reference golden vectors exist,
-SURVEY F10); see oracle/__init__.py.
+Parity status: pinned against the reference's own source files run in the build
+container (tests/golden/ref_loader.py -> tests/golden/reference_*.{json,npz});
+the reference itself ships no golden vectors.  See oracle/__init__.py.
 """
 from __future__ import annotations
 
