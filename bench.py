@@ -124,9 +124,21 @@ def cpu_oracle_clips_per_sec(n_clips: int, warmup: int = 1):
     return n_clips / dt, cores, dt
 
 
-def workload_config(clips_per_gpu: int, world: int) -> dict:
+def clip_tflop(n_frames: int = 8, n_segments: int = 8, faces: bool = False) -> float:
+    """Dense algorithmic TFLOP per clip: 1.875 for C2, 5.764 for C4 (16 frames + 16 faces + 8 s audio)."""
+    return (n_frames * (2 if faces else 1) * GF_VIT_FRAME + n_segments * GF_HUBERT_SEG + GF_FUSE_CLIP) / 1e3
+
+
+def workload_config(clips_per_gpu: int, world: int, n_frames: int = 8, n_segments: int = 8, faces: bool = False) -> dict:
     """`config` of the JSON line; shared by both arms (the reference arm measures the same workload on the host)."""
-    tf_per_clip = (8 * GF_VIT_FRAME + 8 * GF_HUBERT_SEG + GF_FUSE_CLIP) / 1e3
+    tf_per_clip = clip_tflop(n_frames, n_segments, faces)
+    vit_frames = n_frames * (2 if faces else 1)
+    if (n_frames, n_segments, faces) != (8, 8, False):
+        return {"workload": f"{clips_per_gpu} clips/GPU x ({n_frames} frames{' + ' + str(n_frames) + ' face crops' if faces else ''} 224^2 + "
+                            f"{n_segments}x2s 16kHz audio) -> {'frame/face' if faces else 'frame'}/audio/multi tokens @3584 (C4 shape when 16/16/faces)",
+                "clips_per_gpu": clips_per_gpu, "weights": "random-init CLIP ViT-L/14 + HuBERT-large (layer-norm conv) + heads",
+                "cache": "inputs and activations exceed the 126 MB L2", "parallelism": f"dp{world}", "tflop_per_clip": tf_per_clip,
+                "tflop_per_clip_executed": tf_per_clip - (0.0 if os.environ.get("AGB_VIT_DENSE_LAST") == "1" else vit_frames * GF_VIT_FRAME_PRUNED / 1e3)}
     return {"workload": f"C2: {clips_per_gpu} clips/GPU x (8 frames 224^2 + 8x2s 16kHz audio) -> frame/audio/multi tokens @3584",
             "clips_per_gpu": clips_per_gpu, "weights": "random-init CLIP ViT-L/14 + HuBERT-large (layer-norm conv) + heads",
             "cache": "inputs (373 MB/step) and activations exceed the 126 MB L2", "parallelism": f"dp{world}",
@@ -164,6 +176,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=64, help="clips per GPU per step (C2: 64)")
+    ap.add_argument("--n-frames", type=int, default=8, help="frames per clip (C2: 8; C4: 16)")
+    ap.add_argument("--n-segments", type=int, default=8, help="2-second audio segments per clip (C2: 8; C4 with 8 s audio: 16)")
+    ap.add_argument("--with-faces", action="store_true", help="three-stream clips: as many face crops as frames (C4)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,39 +208,48 @@ def main():
     model = agb.build_path(S.clip_state(24, dev), S.hubert_state(24, "layer", dev), S.fusion_state(3584, dev), device=dev,
                            max_frames_per_chunk=512, max_segments_per_chunk=512)
     # host (pinned) and device copies of this rank's batch; frames fp32 0..255 as the reference passes them
-    h_frames = S.frames(B, 8, seed=1000 + rank).pin_memory()
-    h_audio = S.audio(B, 8, seed=2000 + rank).pin_memory()
+    NF, NS, FACES = args.n_frames, args.n_segments, args.with_faces
+    fof = "multiface_audio_face_frame_text" if FACES else "multiframe_audio_frame_text"
+    h_frames = S.frames(B, NF, seed=1000 + rank).pin_memory()
+    h_audio = S.audio(B, NS, seed=2000 + rank).pin_memory()
+    h_faces = S.frames(B, NF, seed=3000 + rank).pin_memory() if FACES else None
     d_frames, d_audio = h_frames.to(dev), h_audio.to(dev)
-    h_tokens = torch.empty((B, 3, 3584), dtype=torch.float32).pin_memory()
+    d_faces = h_faces.to(dev) if FACES else None
+    h_tokens = torch.empty((B, 4 if FACES else 3, 3584), dtype=torch.float32).pin_memory()
     total_clips = B * world
 
     def finish(out):
-        toks = torch.cat([out["multi"], out["audio"], out["frame"]], dim=1)          # [B,3,3584]
+        toks = torch.cat([out["multi"], out["audio"]] + ([out["face"]] if FACES else []) + [out["frame"]], dim=1)   # prompt order
         if world > 1:
             toks = P.gather_clip_rows(toks.contiguous(), total_clips)
         return toks
 
-    def step(frames, audio):                                                         # eager: one launch per kernel
-        return finish(model.encode_clip_batch({"raw_frames": frames, "raw_audios": audio,
-                                               "face_or_frame": "multiframe_audio_frame_text"}))
+    def step(frames, audio, faces=None):                                             # eager: one launch per kernel
+        smp = {"raw_frames": frames, "raw_audios": audio, "face_or_frame": fof}
+        if FACES:
+            smp["raw_faces"] = faces
+        return finish(model.encode_clip_batch(smp))
 
     # the public fast path for a fixed batch shape: the whole step replayed from a CUDA graph (GraphedClipBatch);
     # three instances = the device-resident one + the two upload slots of the end-to-end arm
     use_graph = not args.no_graph
-    graphed = [agb.GraphedClipBatch(model, B, 8, 8, device=dev) for _ in range(3)] if use_graph else None
+    graphed = [agb.GraphedClipBatch(model, B, NF, NS, with_faces=FACES, device=dev) for _ in range(3)] if use_graph else None
     if use_graph:
         graphed[2].raw_frames.copy_(d_frames)
         graphed[2].raw_audios.copy_(d_audio)
+        if FACES:
+            graphed[2].raw_faces.copy_(d_faces)
 
     def step_resident():
-        return finish(graphed[2]()) if use_graph else step(d_frames, d_audio)
+        return finish(graphed[2]()) if use_graph else step(d_frames, d_audio, d_faces)
 
     # end-to-end: every step's inputs come from pinned host memory and its tokens go back to the host inside the timed
     # region; the NEXT step's H2D runs on a copy stream while this step computes (two device input slots), which is
     # what a sweep with a prefetching loader does.  K timed steps = K uploads + K downloads.
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = ([(g.raw_frames, g.raw_audios) for g in graphed[:2]] if use_graph
-             else [(torch.empty_like(d_frames), torch.empty_like(d_audio)) for _ in range(2)])
+    slots = ([(g.raw_frames, g.raw_audios, g.raw_faces) for g in graphed[:2]] if use_graph
+             else [(torch.empty_like(d_frames), torch.empty_like(d_audio), torch.empty_like(d_faces) if FACES else None)
+                   for _ in range(2)])
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     ev_consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -235,6 +259,8 @@ def main():
             copy_stream.wait_event(ev_consumed[sl])                 # the step that last read this slot has finished
             slots[sl][0].copy_(h_frames, non_blocking=True)
             slots[sl][1].copy_(h_audio, non_blocking=True)
+            if FACES:
+                slots[sl][2].copy_(h_faces, non_blocking=True)
             ev_copied[sl].record(copy_stream)
 
     def run_e2e(k):
@@ -245,7 +271,7 @@ def main():
                 upload(i + 1)
             sl = i % 2
             cur.wait_event(ev_copied[sl])
-            toks = finish(graphed[sl]()) if use_graph else step(slots[sl][0], slots[sl][1])
+            toks = finish(graphed[sl]()) if use_graph else step(slots[sl][0], slots[sl][1], slots[sl][2])
             ev_consumed[sl].record(cur)
             h_tokens.copy_(toks[:B] if world > 1 else toks, non_blocking=True)
 
@@ -292,7 +318,7 @@ def main():
     model.overlap_encoders = False          # one stream: every kernel's event pair then brackets that kernel alone
     E.profile_begin()
     for _ in range(args.steps):
-        step(d_frames, d_audio)
+        step(d_frames, d_audio, d_faces)
     prof = E.profile_end()
     model.overlap_encoders = overlap
 
@@ -301,16 +327,17 @@ def main():
     peaks = read_peaks()
     g = prof["gemm"]
     gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
-    tf_per_clip = (8 * GF_VIT_FRAME + 8 * GF_HUBERT_SEG + GF_FUSE_CLIP) / 1e3
+    tf_per_clip = clip_tflop(NF, NS, FACES)
     step_tflops = value / world * tf_per_clip
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": workload_config(B, world),
+        "config": workload_config(B, world, NF, NS, FACES),
         "e2e": {"value": e2e_value, "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(h_frames.numel() * 4 + h_audio.numel() * 4), "d2h_bytes_per_step": int(h_tokens.numel() * 4)},
+                "h2d_bytes_per_step": int((h_frames.numel() + h_audio.numel() + (h_faces.numel() if FACES else 0)) * 4),
+                "d2h_bytes_per_step": int(h_tokens.numel() * 4)},
         "gpu_launches": int(launches), "launch_mode": "cuda-graph replay (GraphedClipBatch)" if use_graph else "eager",
         "encoder_streams": 2 if overlap else 1,
         "roofline": {"bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
@@ -327,7 +354,7 @@ def main():
                      "frontend_gbs": (prof["frontend"]["bytes"] / (prof["frontend"]["ms"] / 1e3) / 1e9) if prof["frontend"]["ms"] > 0 else 0.0},
         "clocks": clk,
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and (NF, NS, FACES) == (8, 8, False):   # the CPU sample is C2-shaped
         cps, cores, dt = cpu_oracle_clips_per_sec(args.cpu_clips, warmup=1)
         line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_clips} clips at batch 1 (oracle: HF fp32 + restated wrappers), 1 warm-up, {dt:.1f} s"}
