@@ -218,6 +218,33 @@ def test_full_config_c1_against_golden():
     model._engine.close()
 
 
+def test_demo_clip_structured_input_against_golden():
+    """a real clip instead of noise - the reference's demo mp4 / wav (decoded frames and PCM travel in the
+    fixture, tests/golden/make_demo_golden.py) through staging (GPU audio slicing), both 24-layer encoders and the heads,
+    against the oracle's features for the same inputs."""
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import staging
+    gold = np.load(os.path.join(GOLD, "golden_demo_clip.npz"))
+    clip = R.build_clip_vision(num_layers=24, seed=1234)
+    hub = R.build_hubert(num_layers=24, feat_extract_norm="layer", seed=1234)
+    model = agb.build_path(clip.state_dict(), hub.state_dict(), R.build_fusion_state(seed=1234), device=DEV)
+    del clip, hub
+    raw = torch.from_numpy(gold["frames_u8"]).permute(3, 0, 1, 2).float()[None].to(DEV)          # [1,3,8,224,224] 0..255
+    wav = torch.from_numpy(gold["pcm_i16"].astype(np.float32) / 32768.0)[None]                   # [1, 55357]
+    segs = staging.stage_audio(wav, device=DEV)                                                   # [8,1,32000] on the GPU
+    out = model.encode_clip_batch({"raw_frames": raw, "raw_audios": segs[None], "face_or_frame": "multiframe_audio_frame_text"})
+    gate(out["frame_hiddens"], torch.from_numpy(gold["frame_hidden"]), "demo frame hiddens")
+    gate(out["audio_hiddens"], torch.from_numpy(gold["audio_hidden"]), "demo audio hiddens")
+    for k in ("frame", "audio", "multi"):
+        gate(out[k], torch.from_numpy(gold[f"token_{k}"]), f"demo token[{k}]")
+    # the uint8 entry point of the engine (what the sweep CLI uses) sees the same frames
+    u8 = torch.from_numpy(gold["frames_u8"]).permute(0, 3, 1, 2).contiguous().to(DEV)
+    assert torch.equal(model._engine.clip_forward(u8), out["frame_hiddens"][0])
+    assert R.nn_identity(out["frame_hiddens"][0].cpu(), torch.from_numpy(gold["frame_hidden"][0]))
+    assert R.nn_identity(out["audio_hiddens"][0].cpu(), torch.from_numpy(gold["audio_hidden"][0]))
+    model._engine.close()
+
+
 def test_batch_of_clips_equals_clip_by_clip(small_path):
     """Clips are independent (the data-parallel premise): a batch equals its clips run one at a time."""
     model, _, _, _ = small_path

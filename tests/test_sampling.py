@@ -79,3 +79,18 @@ def test_smart_indices_example():
     au = {"peak_frames": [{"peak_index": 40, "frames_before_peak": 3, "frames_after_peak": 3}], "total_frames": 88}
     got = O.smart_frame_indices(au, 88)
     assert {38, 39, 40, 41, 42} <= set(got) and len(got) == 8 and got == sorted(got)
+
+
+def test_demo_clip_fixture_follows_the_reference_rules():
+    """tests/golden/golden_demo_clip.npz (made from A/demo/sample_00000000.{mp4,wav}): 8 frames at the uniform indices of an
+    88-frame video, 55 357 PCM samples whose eight 2-second slices start where SURVEY 8a-a4 says."""
+    import os
+    import numpy as np
+    from affectgpt_b200 import sampling
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_demo_clip.npz"))
+    assert gold["frames_u8"].shape == (8, 224, 224, 3) and gold["frames_u8"].dtype == np.uint8
+    assert gold["pcm_i16"].shape == (55357,)
+    assert sampling.uniform_frame_indices(88, 8) == [0, 11, 22, 33, 44, 55, 66, 77]
+    assert [a for a, _ in sampling.audio_segment_bounds(55357, 16000, 2, 8)] == [0, 3336, 6673, 10010, 13346, 16683, 20020, 23356]
+    assert gold["frame_hidden"].shape == (1, 8, 768) and gold["audio_hidden"].shape == (1, 8, 1024)
+    assert gold["token_multi"].shape == (1, 1, 3584) and np.isfinite(gold["token_multi"]).all()
