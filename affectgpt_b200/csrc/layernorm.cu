@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) ln512_bf16_kernel(const bf16* x, long lon
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       y[i] = (f[h * 8 + i] - mean) * rstd * gg[i] + bb[i];
-      if (apply_gelu) y[i] = AGB_GELU_ERF(y[i]);
+      if (apply_gelu) y[i] = gelu_erf_tanhform(y[i]);
     }
     uint4 o;
     o.x = pack_bf16x2(y[0], y[1]);
