@@ -47,6 +47,7 @@ SIGNATURES = {
                                 C.POINTER(_vp), _vp, _vp]),
     "agb_stage_faces": (_i, [_vp, _i64, _i, _i, _vp, _i, _vp, _vp]),
     "agb_stage_audio": (_i, [_vp, _i, _i64, _vp, _i, _i, _vp, _vp]),
+    "agb_resample_audio": (_i, [_vp, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "agb_qformer_fuse": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "agb_set_tap": (_i, [_vp, C.c_char_p, _vp, _i64]),
     "agb_launch_count": (_i64, []),

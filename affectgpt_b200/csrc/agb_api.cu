@@ -888,6 +888,11 @@ int agb_stage_audio(const float* wav, int ch, int64_t n, const int64_t* starts, 
                          static_cast<cudaStream_t>(stream));
 }
 
+int agb_resample_audio(const float* wav, int ch, int64_t n, const float* bank, int orig, int nw, int width, int taps,
+                       float* out, int64_t n_out, void* stream) {
+  return resample_f32(wav, ch, n, bank, orig, nw, width, taps, out, n_out, static_cast<cudaStream_t>(stream));
+}
+
 // ---- kernel-level entry points ---------------------------------------------------------------
 int agb_op_gemm(int a_mode, int act, const void* A, int64_t lda, const void* W, int M, int N, int K, const float* bias,
                 const float* res, int64_t ld_res, float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, int nseq,

@@ -174,6 +174,10 @@ int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int*
 int stage_audio_f32(const float* wav, int ch, int64_t n, const long long* starts_dev, int clips, int clip_len, float* out,
                     cudaStream_t s);
 
+// wav [ch,n] f32 -> out [ch,n_out]: polyphase sinc FIR, bank [nw, taps = 2*width + orig] (torchaudio.functional.resample)
+int resample_f32(const float* wav, int ch, int64_t n, const float* bank, int orig, int nw, int width, int taps, float* out,
+                 int64_t n_out, cudaStream_t s);
+
 // splice.cu ----------------------------------------------------------------------------------
 // in-place on embeds [B,L,D] (fp32 or bf16); status [B,n_mod,3] = {count, first position or -1, consecutive}
 int splice_tokens(void* embeds_inout, int dtype, const long long* ids, int B, int L, int D, int n_mod,

@@ -73,7 +73,43 @@ __global__ void __launch_bounds__(256) audio_gather_kernel(const float* __restri
   }
 }
 
+// Polyphase sinc resampling (torchaudio.functional.resample, called by load_audio at ImageBind/data.py:186-187):
+//   y[c, j * new + p] = sum_k bank[p, k] * xpad[c, j * orig + k],   xpad[i] = x[i - width] (zero outside [0, n)),
+// bank [new, taps] with taps = 2 * width + orig (built on the host with torchaudio's formula).  One thread per output
+// sample, k ascending in fp32; the phase rows of a block's outputs sit in shared memory when they fit.
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, long long n, const float* __restrict__ bank,
+                                                       int orig, int nw, int width, int taps, float* __restrict__ y,
+                                                       long long n_out) {
+  const int c = blockIdx.y;
+  const float* xc = x + (long long)c * n;
+  for (long long o = (long long)blockIdx.x * 256 + threadIdx.x; o < n_out; o += (long long)gridDim.x * 256) {
+    const long long j = o / nw;
+    const int p = (int)(o - j * nw);
+    const float* bp = bank + (long long)p * taps;
+    const long long base = j * orig - width;
+    float acc = 0.f;
+    for (int k = 0; k < taps; ++k) {
+      const long long i = base + k;
+      const float v = (i >= 0 && i < n) ? __ldg(xc + i) : 0.f;
+      acc = fmaf(__ldg(bp + k), v, acc);
+    }
+    y[(long long)c * n_out + o] = acc;
+  }
+}
+
 }  // namespace
+
+int resample_f32(const float* wav, int ch, int64_t n, const float* bank, int orig, int nw, int width, int taps, float* out,
+                 int64_t n_out, cudaStream_t s) {
+  AGB_REQUIRE(wav && bank && out && ch >= 1 && n > 0 && n_out > 0, "resample: bad arguments");
+  AGB_REQUIRE(orig > 0 && nw > 0 && width > 0 && taps == 2 * width + orig, "resample: bad filter bank shape");
+  LaunchTimer timer(PROF_FRONTEND, 2.0 * ch * n_out * taps, 4.0 * ch * (n + n_out), s);
+  long long blocks = (n_out + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  resample_kernel<<<dim3((unsigned)blocks, (unsigned)ch), 256, 0, s>>>(wav, n, bank, orig, nw, width, taps, out, n_out);
+  AGB_CHECK_LAUNCH();
+  return 0;
+}
 
 int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int* idx_dev, int T, uint8_t* out,
                    cudaStream_t s) {

@@ -102,8 +102,9 @@ def read_video_frames(video_path: str, pick: Callable[[int], List[int]]) -> np.n
     return np.stack([cv2.resize(cv2.cvtColor(frames[i], cv2.COLOR_BGR2RGB), (224, 224)) for i in idx])
 
 
-def read_wav(audio_path: str, sample_rate: int = 16000) -> torch.Tensor:
-    """-> float32 [channels, n] at ``sample_rate`` (torchaudio.load semantics: int PCM scaled to [-1, 1))."""
+def read_wav(audio_path: str):
+    """-> (float32 [channels, n], sample rate of the file) with torchaudio.load semantics (int PCM scaled to [-1, 1));
+    resampling to 16 kHz (data.py:186-187) happens on the GPU in ``staging.stage_audio``."""
     from scipy.io import wavfile
     sr, data = wavfile.read(audio_path)
     if data.dtype == np.int16:
@@ -114,11 +115,7 @@ def read_wav(audio_path: str, sample_rate: int = 16000) -> torch.Tensor:
         wav = (data.astype(np.float32) - 128.0) / 128.0
     else:
         wav = data.astype(np.float32)
-    wav = torch.from_numpy(np.ascontiguousarray(wav.T if wav.ndim == 2 else wav[None]))
-    if sr != sample_rate:                                  # data.py:186-187
-        import torchaudio
-        wav = torchaudio.functional.resample(wav, orig_freq=sr, new_freq=sample_rate)
-    return wav
+    return torch.from_numpy(np.ascontiguousarray(wav.T if wav.ndim == 2 else wav[None])), int(sr)
 
 
 # --------------------------------------------------------------------------------------------- extractor
@@ -157,7 +154,8 @@ class MultimodalFeatureExtractor:
 
     def extract_audio_features(self, audio_path, clips_per_video=8):
         try:
-            raw = staging.stage_audio(read_wav(audio_path), clips_per_video=clips_per_video, device=self.device)
+            wav, sr = read_wav(audio_path)
+            raw = staging.stage_audio(wav, clips_per_video=clips_per_video, device=self.device, orig_sample_rate=sr)
             with torch.no_grad():
                 feats = self.encoders["acoustic"](None, raw[None])                               # [1,T,1024]
             return feats[0].float().cpu().numpy()
@@ -198,8 +196,8 @@ class MultimodalFeatureExtractor:
             print(f"Error extracting face features from {face_npy_path}: {e}")
             return None
 
-    def decode_audio(self, audio_path) -> Optional[torch.Tensor]:
-        """-> float32 [channels, n] at 16 kHz (host)."""
+    def decode_audio(self, audio_path):
+        """-> (float32 [channels, n], sample rate) on the host."""
         try:
             return read_wav(audio_path)
         except Exception:
@@ -242,7 +240,8 @@ class MultimodalFeatureExtractor:
                 if d.get("audio") is None:
                     continue
                 try:
-                    segs.append(staging.stage_audio(d["audio"], clips_per_video=clips_per_video, device=dev))
+                    wav, sr = d["audio"]
+                    segs.append(staging.stage_audio(wav, clips_per_video=clips_per_video, device=dev, orig_sample_rate=sr))
                     st["audio_owner"].append(i)
                 except Exception:
                     pass

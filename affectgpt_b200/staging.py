@@ -1,8 +1,8 @@
 """GPU-side input staging with the reference's loader signatures.
 
 Reference: ``load_face`` (A/my_affectgpt/processors/video_processor.py:262-296) and ``load_audio``
-(A/my_affectgpt/models/ImageBind/data.py:170-214).  Decoding (np.load / torchaudio / decord) and resampling stay with
-the caller; what moves to the device is everything after it: the cv2-exact bilinear resize of the *sampled* face crops
+(A/my_affectgpt/models/ImageBind/data.py:170-214).  Decoding (np.load / torchaudio / decord) stays with the caller; what
+X
 (the reference resizes every crop on the CPU and then samples 8), the mono mix-down, the 2-second zero padding and the
 eight-slice gather.  Index rules run on the host and are bit-exact (``sampling``).  No CPU fallback.
 """
@@ -64,13 +64,70 @@ def load_face(faces: Union[str, np.ndarray, torch.Tensor], n_frms: int = 8, heig
     return u8.permute(1, 0, 2, 3).to(torch.float32)                  # '(C, T, H, W)' float, :292-293
 
 
-def stage_audio(waveform: torch.Tensor, sample_rate: int = 16000, clip_duration: int = 2, clips_per_video: int = 8,
-                device="cuda:0") -> torch.Tensor:
-    """waveform [channels, n] float32 at ``sample_rate`` (already resampled) -> [clips,1,clip_duration*sample_rate] on
-    ``device`` (data.py:188-212: two channels are averaged, waveforms shorter than one clip are zero-padded)."""
+_BANKS: dict = {}
+
+
+def resample_bank(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """The windowed-sinc filter bank of ``torchaudio.functional.resample`` (sinc_interp_hann, its defaults - what
+    ``load_audio`` calls at ImageBind/data.py:186-187), restated with the same float32 torch operations in the same
+    order: -> (bank [new, 2*width + orig] float32 on the host, orig // gcd, new // gcd, width)."""
+    import math
+    if int(orig_freq) != orig_freq or int(new_freq) != new_freq or orig_freq <= 0 or new_freq <= 0:
+        raise ValueError("sample rates must be positive integers")
+    key = (int(orig_freq), int(new_freq), lowpass_filter_width, rolloff)
+    if key in _BANKS:
+        return _BANKS[key]
+    gcd = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // gcd, int(new_freq) // gcd
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    dt = torch.float32                                                  # resample() passes waveform.dtype
+    idx = torch.arange(-width, width + orig, dtype=dt)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=dt)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lowpass_filter_width, lowpass_filter_width)
+    window = torch.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t *= math.pi
+    scale = base_freq / orig
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * scale
+    out = (kernels[:, 0, :].contiguous(), orig, new, width)
+    _BANKS[key] = out
+    return out
+
+
+def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int = 16000, device="cuda:0") -> torch.Tensor:
+    """``torchaudio.functional.resample(waveform, orig_freq, new_freq)`` on the GPU: [channels, n] -> [channels,
+    ceil(new * n / orig)] float32 on ``device`` (same filter bank, fp32 FIR; differs from torchaudio's conv1d only by
+    the summation order)."""
+    import math
     dev = _cuda(device)
     if waveform.dim() != 2:
         raise ValueError(f"expected [channels, samples], got {tuple(waveform.shape)}")
+    wav = waveform.to(device=dev, dtype=torch.float32).contiguous()
+    if int(orig_freq) == int(new_freq):
+        return wav
+    bank, orig, new, width = resample_bank(orig_freq, new_freq)
+    ch, n = wav.shape
+    n_out = int(math.ceil(new * n / orig))
+    bank_d = bank.to(dev)
+    out = torch.empty((ch, n_out), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().agb_resample_audio(wav.data_ptr(), ch, n, bank_d.data_ptr(), orig, new, width, bank.shape[1],
+                                                  out.data_ptr(), n_out, _stream(dev)), None, "agb_resample_audio")
+    return out
+
+
+def stage_audio(waveform: torch.Tensor, sample_rate: int = 16000, clip_duration: int = 2, clips_per_video: int = 8,
+                device="cuda:0", orig_sample_rate: int = None) -> torch.Tensor:
+    """waveform [channels, n] float32 -> [clips,1,clip_duration*sample_rate] on ``device`` (data.py:186-212: resampled to
+    ``sample_rate`` when ``orig_sample_rate`` differs, two channels averaged, waveforms shorter than one clip
+    zero-padded)."""
+    dev = _cuda(device)
+    if waveform.dim() != 2:
+        raise ValueError(f"expected [channels, samples], got {tuple(waveform.shape)}")
+    if orig_sample_rate is not None and int(orig_sample_rate) != int(sample_rate):
+        waveform = resample(waveform, int(orig_sample_rate), int(sample_rate), dev)
     ch, n = waveform.shape
     wav = waveform.to(device=dev, dtype=torch.float32).contiguous()
     clip_len = clip_duration * sample_rate

@@ -100,6 +100,12 @@ int agb_qformer_fuse(agb_ctx* ctx, int which, const float* Hv, int Tv, const flo
 int agb_stage_faces(const void* faces_u8, int64_t n_src, int h, int w, const int32_t* idx, int T, void* out_u8, void* stream);
 int agb_stage_audio(const float* wav, int ch, int64_t n, const int64_t* starts, int clips, int clip_len, float* out,
                     void* stream);
+/* agb_resample_audio: the torchaudio.functional.resample call of load_audio (ImageBind/data.py:186-187) - wav [ch,n] f32 at
+ *   the file's rate -> out [ch,n_out] f32 at 16 kHz, n_out = ceil(new * n / orig) with orig / new the rates divided by
+ *   their gcd; bank [new, taps] f32, taps = 2 * width + orig, is torchaudio's windowed-sinc filter bank (built by the host:
+ *   affectgpt_b200.staging.resample_bank). */
+int agb_resample_audio(const float* wav, int ch, int64_t n, const float* bank, int orig, int nw, int width, int taps,
+                       float* out, int64_t n_out, void* stream);
 
 /* Token splice (AffectGPT.forward, affectgpt.py:956-1009): in place on embeds [B,L,D] (AGB_DTYPE_F32 / AGB_DTYPE_BF16).
  * input_ids [B,L] int64 (device); token_ids / n_query / mod_embeds are HOST arrays of n_mod (<= 8) entries, mod_embeds[i]

@@ -29,7 +29,7 @@ def _write_dataset(root, names):
         np.save(f / n / f"{n}.npy", faces)
         nsamp = [55357, 30000, 96000][i % 3]
         pcm = (rng.standard_normal((nsamp, 2 if i == 1 else 1)) * 3000 * (1 + i)).astype(np.int16)
-        wavfile.write(a / f"{n}.wav", 16000, pcm if i == 1 else pcm[:, 0])
+        wavfile.write(a / f"{n}.wav", 44100 if i == 4 else 16000, pcm if i == 1 else pcm[:, 0])    # sample 4: resampled on the GPU
         data[n] = (frames, faces, pcm)
     (root / "names.txt").write_text("\n".join(names + ["missing_everything"]) + "\n")
     return data

@@ -9,6 +9,7 @@ import torch
 
 from oracle import qformer as OQ
 from oracle import reference_path as R
+from oracle import sampling as OS
 from tests.gpu_util import gate
 
 pytestmark = pytest.mark.gpu
@@ -192,3 +193,21 @@ def test_gpu_splice_raises_like_reference():
     ids3 = torch.full((2, 16), 7)
     out = P.splice_tokens(emb, ids3, TOK, nq, feats)         # no placeholders: identity
     assert torch.equal(out, emb)
+
+
+@pytest.mark.parametrize("orig,n,ch", [(44100, 97531, 1), (48000, 120000, 2), (22050, 30011, 1), (8000, 15999, 1), (11025, 40000, 2)])
+def test_gpu_resample_matches_torchaudio(orig, n, ch):
+    """agb_resample_audio vs torchaudio.functional.resample (what load_audio calls, data.py:186-187): same filter bank,
+    fp32 FIR - equal up to the summation order; then the staged 2-second slices of the resampled waveform."""
+    F = pytest.importorskip("torchaudio.functional")
+    from affectgpt_b200 import staging
+    g = torch.Generator().manual_seed(orig + n)
+    wav = torch.randn(ch, n, generator=g) * 0.3
+    want = F.resample(wav, orig_freq=orig, new_freq=16000)
+    got = staging.resample(wav, orig, 16000, DEV).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max()))
+    segs = staging.stage_audio(wav, device=DEV, orig_sample_rate=orig).cpu()
+    ref_segs, _ = OS.audio_segments(want)
+    assert segs.shape == ref_segs.shape
+    assert float((segs - ref_segs).abs().max()) <= 2e-6

@@ -76,3 +76,20 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_resample_filter_bank_is_torchaudios():
+    """staging.resample_bank restates torchaudio.functional.resample's windowed-sinc bank (the call load_audio makes at
+    ImageBind/data.py:186-187) with the same float32 operations: identical taps, width and phase count."""
+    import math
+    import pytest
+    import torch
+    from affectgpt_b200 import staging
+    F = pytest.importorskip("torchaudio.functional.functional")
+    for orig, new in ((44100, 16000), (48000, 16000), (22050, 16000), (8000, 16000), (11025, 16000), (32000, 16000)):
+        bank, o, n, width = staging.resample_bank(orig, new)
+        ref, ref_width = F._get_sinc_resample_kernel(orig, new, math.gcd(orig, new), dtype=torch.float32)
+        assert width == ref_width and (o, n) == (orig // math.gcd(orig, new), new // math.gcd(orig, new))
+        assert bank.shape == (n, 2 * width + o) and torch.equal(bank, ref[:, 0, :])
+    with pytest.raises(ValueError):
+        staging.resample_bank(44100.5, 16000)
