@@ -102,20 +102,7 @@ def read_video_frames(video_path: str, pick: Callable[[int], List[int]]) -> np.n
     return np.stack([cv2.resize(cv2.cvtColor(frames[i], cv2.COLOR_BGR2RGB), (224, 224)) for i in idx])
 
 
-def read_wav(audio_path: str):
-    """-> (float32 [channels, n], sample rate of the file) with torchaudio.load semantics (int PCM scaled to [-1, 1));
-    resampling to 16 kHz (data.py:186-187) happens on the GPU in ``staging.stage_audio``."""
-    from scipy.io import wavfile
-    sr, data = wavfile.read(audio_path)
-    if data.dtype == np.int16:
-        wav = data.astype(np.float32) / 32768.0
-    elif data.dtype == np.int32:
-        wav = data.astype(np.float32) / 2147483648.0
-    elif data.dtype == np.uint8:
-        wav = (data.astype(np.float32) - 128.0) / 128.0
-    else:
-        wav = data.astype(np.float32)
-    return torch.from_numpy(np.ascontiguousarray(wav.T if wav.ndim == 2 else wav[None])), int(sr)
+read_wav = staging.read_wav          # wav decode lives next to the loader it feeds (staging.load_audio)
 
 
 # --------------------------------------------------------------------------------------------- extractor

@@ -67,6 +67,22 @@ def load_face(faces: Union[str, np.ndarray, torch.Tensor], n_frms: int = 8, heig
 _BANKS: dict = {}
 
 
+def read_wav(audio_path: str):
+    """-> (float32 [channels, n], sample rate of the file) with torchaudio.load semantics (int PCM scaled to [-1, 1));
+    resampling to 16 kHz (data.py:186-187) happens on the GPU in ``staging.stage_audio``."""
+    from scipy.io import wavfile
+    sr, data = wavfile.read(audio_path)
+    if data.dtype == np.int16:
+        wav = data.astype(np.float32) / 32768.0
+    elif data.dtype == np.int32:
+        wav = data.astype(np.float32) / 2147483648.0
+    elif data.dtype == np.uint8:
+        wav = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        wav = data.astype(np.float32)
+    return torch.from_numpy(np.ascontiguousarray(wav.T if wav.ndim == 2 else wav[None])), int(sr)
+
+
 def resample_bank(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
     """The windowed-sinc filter bank of ``torchaudio.functional.resample`` (sinc_interp_hann, its defaults - what
     ``load_audio`` calls at ImageBind/data.py:186-187), restated with the same float32 torch operations in the same
@@ -138,3 +154,16 @@ def stage_audio(waveform: torch.Tensor, sample_rate: int = 16000, clip_duration:
         _lib.check(_lib.load().agb_stage_audio(wav.data_ptr(), ch, n, starts.data_ptr(), clips_per_video, clip_len,
                                                out.data_ptr(), _stream(dev)), None, "agb_stage_audio")
     return out
+
+
+def load_audio(audio_paths, device, sample_rate: int = 16000, clip_duration: int = 2, clips_per_video: int = 8):
+    """Drop-in for the reference's ``load_audio`` (ImageBind/data.py:170-214): wav files -> [n, clips, 1,
+    clip_duration * sample_rate] float32 on ``device``.  The files are decoded on the host (scipy; the reference uses
+    torchaudio.load); resampling, mono mix-down, padding and slicing run on the GPU."""
+    if audio_paths is None:
+        return None
+    outs = []
+    for path in audio_paths:
+        wav, sr = read_wav(path)
+        outs.append(stage_audio(wav, sample_rate, clip_duration, clips_per_video, device, orig_sample_rate=sr))
+    return torch.stack(outs, dim=0)

@@ -211,3 +211,27 @@ def test_gpu_resample_matches_torchaudio(orig, n, ch):
     ref_segs, _ = OS.audio_segments(want)
     assert segs.shape == ref_segs.shape
     assert float((segs - ref_segs).abs().max()) <= 2e-6
+
+
+def test_load_audio_drop_in(tmp_path):
+    """staging.load_audio(paths, device) == the reference's load_audio: one 16 kHz mono file, one 44.1 kHz stereo file,
+    one shorter than 2 s; compared with torchaudio.functional.resample + the restated slicing."""
+    F = pytest.importorskip("torchaudio.functional")
+    from scipy.io import wavfile
+    from affectgpt_b200 import staging
+    rng = np.random.default_rng(3)
+    specs = [(16000, 55357, 1), (44100, 150000, 2), (16000, 20000, 1)]
+    paths, want = [], []
+    for i, (sr, n, ch) in enumerate(specs):
+        pcm = (rng.standard_normal((n, ch)) * 4000).astype(np.int16)
+        path = str(tmp_path / f"a{i}.wav")
+        wavfile.write(path, sr, pcm if ch == 2 else pcm[:, 0])
+        paths.append(path)
+        wav = torch.from_numpy(pcm.astype(np.float32) / 32768.0).T.contiguous()
+        if sr != 16000:
+            wav = F.resample(wav, orig_freq=sr, new_freq=16000)
+        want.append(OS.audio_segments(wav)[0])
+    got = staging.load_audio(paths, DEV)
+    assert got.device.type == "cuda" and tuple(got.shape) == (3, 8, 1, 32000)
+    assert float((got.cpu() - torch.stack(want)).abs().max()) <= 2e-6
+    assert staging.load_audio(None, DEV) is None
