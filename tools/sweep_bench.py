@@ -19,7 +19,8 @@ from affectgpt_b200 import extract as X, synthetic as S  # noqa: E402
 N = int(os.environ.get("SWEEP_CLIPS", "384"))
 N_SINGLE = int(os.environ.get("SWEEP_CLIPS_SINGLE", "48"))
 BATCH = int(os.environ.get("SWEEP_BATCH", "64"))
-dev = "cuda:0"
+RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+dev = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
 
 
 def write_dataset(root, n):
@@ -40,7 +41,13 @@ def write_dataset(root, n):
 
 
 def main():
-    root = tempfile.mkdtemp(prefix="agb_sweep_")
+    """Under torchrun every rank sweeps its own N samples (what `python -m affectgpt_b200.extract` does with samples
+    rank::world): no collective on the data path, a barrier on both sides of the timed region, time = max over ranks."""
+    root = tempfile.mkdtemp(prefix=f"agb_sweep_r{RANK}_")
+    if WORLD > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     try:
         names = write_dataset(root, N)
         model = agb.build_path(S.clip_state(24, dev), S.hubert_state(24, "layer", dev), S.fusion_state(3584, dev), device=dev)
@@ -61,21 +68,34 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         res["per_sample_loop"] = {"clips": N_SINGLE, "seconds": dt, "clips_per_s": N_SINGLE / dt, "stats": st}
-        print(f"per-sample loop : {N_SINGLE / dt:7.1f} clips/s ({N_SINGLE} clips, {dt:.1f} s)", flush=True)
+        if RANK == 0:
+            print(f"per-sample loop : {N_SINGLE / dt:7.1f} clips/s per GPU ({N_SINGLE} clips, {dt:.1f} s)", flush=True)
+        if WORLD > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         st = X.run_sweep_batched(args_for("batched", BATCH), ex, names, batch_size=BATCH, workers=16, log=lambda *_: None)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        res["batched"] = {"clips": N, "seconds": dt, "clips_per_s": N / dt, "stats": st}
-        print(f"batched ({BATCH:3d})   : {N / dt:7.1f} clips/s ({N} clips, {dt:.1f} s)", flush=True)
+        if WORLD > 1:
+            tmax = torch.tensor([dt], device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax)
+        res["batched"] = {"clips": N * WORLD, "gpus": WORLD, "seconds": dt, "clips_per_s": N * WORLD / dt, "stats_rank0": st}
+        if RANK == 0:
+            print(f"batched ({BATCH:3d})   : {N * WORLD / dt:7.1f} clips/s on {WORLD} GPU(s) ({N * WORLD} clips, {dt:.1f} s)", flush=True)
         same = all(np.array_equal(np.load(f"{root}/single/mer2024/{sub}/{nm}.npy"), np.load(f"{root}/batched/mer2024/{sub}/{nm}.npy"))
                    for sub in os.listdir(f"{root}/single/mer2024") for nm in names[:N_SINGLE])
         res["files_identical"] = bool(same)
-        print("files identical:", same)
-        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
-        os.makedirs(out, exist_ok=True)
-        json.dump(res, open(os.path.join(out, "sweep_bench.json"), "w"), indent=1)
-        print(json.dumps(res))
+        if RANK == 0:
+            print("files identical:", same)
+            out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            json.dump(res, open(os.path.join(out, f"sweep_bench_n{WORLD}.json"), "w"), indent=1)
+            print(json.dumps(res))
+        if WORLD > 1:
+            dist.barrier()
+            dist.destroy_process_group()
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
