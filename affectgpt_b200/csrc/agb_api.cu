@@ -430,26 +430,38 @@ int ensure_fuse_ws(agb_ctx* c, int64_t B) {
 
 // ------------------------------------------------------------------------------------ encoder block
 // pre-LN transformer block shared by CLIP (quick_gelu) and HuBERT stable-LN (erf GELU)
+// Every tensor between two kernels of a block (0.3-1.1 GB) is larger than the 126 MB L2, but the LAST ~100 MB a producer
+// wrote are still there when its consumer starts.  The kernels of a chain therefore walk their rows in alternating
+// directions ("zigzag", `flip` toggles per launch): a consumer begins with the rows its producer finished with and reads them
+// from L2 instead of HBM.  Results do not depend on the order (AGB_ZIGZAG=0 switches it off for A/B runs).
+bool zigzag_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("AGB_ZIGZAG"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* attn, bf16* h1, int64_t M, int nseq,
-                  int seq_stride, int seq_valid, int act, cudaStream_t s) {
-  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnA_g, L.lnA_b, 1e-5f, xln, 1024, nullptr, 0, s)) return r;
+                  int seq_stride, int seq_valid, int act, cudaStream_t s, bool& flip) {
+  const bool zz = zigzag_on();
+  auto dir = [&]() { const bool r = zz && flip; flip = !flip; return r; };
+  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnA_g, L.lnA_b, 1e-5f, xln, 1024, nullptr, 0, s, dir())) return r;
   GemmArgs g;
   g.A = xln; g.lda = 1024; g.W = L.wqkv; g.M = (int)M; g.N = 3072; g.K = 1024; g.bias = L.bqkv;
-  g.out_bf16 = qkv; g.ld_bf16 = 3072;
+  g.out_bf16 = qkv; g.ld_bf16 = 3072; g.reverse = dir();
   if (int r = gemm_bf16(g, s)) return r;
-  if (int r = attention_mha16x64(qkv, attn, nseq, seq_stride, seq_valid, 0.125f, s)) return r;
+  if (int r = attention_mha16x64(qkv, attn, nseq, seq_stride, seq_valid, 0.125f, s, dir())) return r;
   g = GemmArgs();
   g.A = attn; g.lda = 1024; g.W = L.wo; g.M = (int)M; g.N = 1024; g.K = 1024; g.bias = L.bo;
-  g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024;
+  g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024; g.reverse = dir();
   if (int r = gemm_bf16(g, s)) return r;
-  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnB_g, L.lnB_b, 1e-5f, xln, 1024, nullptr, 0, s)) return r;
+  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnB_g, L.lnB_b, 1e-5f, xln, 1024, nullptr, 0, s, dir())) return r;
   g = GemmArgs();
   g.A = xln; g.lda = 1024; g.W = L.w1; g.M = (int)M; g.N = 4096; g.K = 1024; g.bias = L.b1; g.act = act;
-  g.out_bf16 = h1; g.ld_bf16 = 4096;
+  g.out_bf16 = h1; g.ld_bf16 = 4096; g.reverse = dir();
   if (int r = gemm_bf16(g, s)) return r;
   g = GemmArgs();
   g.A = h1; g.lda = 4096; g.W = L.w2; g.M = (int)M; g.N = 1024; g.K = 4096; g.bias = L.b2;
-  g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024;
+  g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024; g.reverse = dir();
   return gemm_bf16(g, s);
 }
 
@@ -496,13 +508,14 @@ int clip_chunk(agb_ctx* c, const void* frames, int in_dtype, int64_t F, float* o
   // the last block is pruned to the CLS row unless the caller wants it dense (cfg) or taps its full output
   const int last = c->cfg.vit_layers - 1;
   const bool dense_last = c->cfg.vit_dense_last_block != 0 || c->taps.count("vit.block" + std::to_string(last)) != 0;
+  bool flip = true;        // embed_preln wrote the rows in ascending order: the first LayerNorm starts from the end
   for (int l = 0; l < c->cfg.vit_layers; ++l) {
     if (l == last && !dense_last) {
       if (int r = vit_last_block_cls(c, c->v_layers[l], F, s)) return r;
       break;
     }
     if (int r = encoder_block(c->v_layers[l], c->v_resid, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, M, (int)F, 257, 257,
-                              ACT_QUICK_GELU, s))
+                              ACT_QUICK_GELU, s, flip))
       return r;
     tap(c, "vit.block" + std::to_string(l), c->v_resid, M * 1024 * 4, s);
   }
@@ -556,13 +569,14 @@ int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t 
   tap(c, "hubert.posconv", c->h_resid, M * 1024 * 4, s);
   const int L = c->cfg.hubert_layers;
   bool first_pool = true;
+  bool flip = true;
   for (int l = 0; l < L; ++l) {
     if (l >= L - 3) {  // hidden_states[-4], [-3], [-2] = residual stream entering layers L-3, L-2, L-1
       if (int r = seq_mean_pool(c->h_resid, (int)G, 100, 99, nullptr, nullptr, 0.f, 0.25f, first_pool ? 0 : 1, out, s)) return r;
       first_pool = false;
     }
     if (int r = encoder_block(c->h_layers[l], c->h_resid, c->h_xln, c->h_qkv, c->h_attn, c->h_h1, M, (int)G, 100, 99,
-                              ACT_GELU_ERF, s))
+                              ACT_GELU_ERF, s, flip))
       return r;
     tap(c, "hubert.block" + std::to_string(l), c->h_resid, M * 1024 * 4, s);
   }

@@ -77,6 +77,8 @@ struct GemmArgs {
   int64_t ld_bf16 = 0;
   // POSCONV only
   int nseq = 0, seq_stride = 0, seq_valid = 0;
+  // walk the tiles from the last row block to the first (see encoder_block: consumers start where the producer finished)
+  bool reverse = false;
 };
 
 // tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns 0 on success.
@@ -87,7 +89,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 // row stride ldx; writes bf16 and/or fp32.
 int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const float* gamma, const float* beta,
                      float eps, bf16* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32,
-                     cudaStream_t s);
+                     cudaStream_t s, bool reverse = false);
 // in-place over bf16 rows of 512 channels: y = act(LN(x)) (HuBERT conv stack, "layer" variant)
 int layernorm512_bf16_gelu(bf16* x, int64_t rows, const float* gamma, const float* beta, float eps,
                            bool apply_gelu, bf16* out, cudaStream_t s);
@@ -95,11 +97,12 @@ int layernorm512_bf16_gelu(bf16* x, int64_t rows, const float* gamma, const floa
 // attention.cu -------------------------------------------------------------------------------
 // qkv: [nseq * seq_stride, 3*1024] bf16 (q | k | v, 16 heads x 64); out: [nseq * seq_stride, 1024] bf16
 int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale,
-                       cudaStream_t s);
+                       cudaStream_t s, bool reverse = false);
 
 // attention_tc2.cu: tcgen05 path (S / P / O in TMEM, two CTAs per SM); returns -1 when no instantiation covers the
 // shape (the caller then falls back to the mma.sync kernel)
-int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s);
+int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s,
+                  bool reverse = false);
 
 // vit.cu -------------------------------------------------------------------------------------
 int vit_patchify(const void* frames, int in_dtype /*0=f32 0..255, 1=u8*/, int64_t nframes, bf16* a_patch /*[n*256,640]*/,

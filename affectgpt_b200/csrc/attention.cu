@@ -187,7 +187,7 @@ int launch_mha(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_val
 }  // namespace
 
 int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool reverse) {
   AGB_REQUIRE(nseq > 0 && seq_valid > 0 && seq_stride >= seq_valid, "attention: bad sequence shape");
   AGB_REQUIRE(nseq <= 65535, "attention: too many sequences for one launch");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
@@ -200,7 +200,7 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
     force_hmma = (e != nullptr && e[0] == 'h') ? 1 : 0;
   }
   if (!force_hmma) {
-    const int r = attention_tc2(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+    const int r = attention_tc2(qkv, out, nseq, seq_stride, seq_valid, scale, s, reverse);
     if (r >= 0) return r;
   }
   if (seq_valid <= 112) return launch_mha<7>(qkv, out, nseq, seq_stride, seq_valid, scale, s);

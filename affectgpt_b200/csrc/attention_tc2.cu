@@ -121,6 +121,7 @@ __host__ __device__ constexpr uint32_t idesc_bf16(uint32_t m, uint32_t n, uint32
 
 struct AParams {
   int nseq, seq_stride, seq_valid, qtiles;
+  int reverse;             // items (sequence, head) from the last to the first
   int stray_q;             // 1: query row NMAIN of every sequence is computed by the softmax warps on the CUDA cores
   float scale_log2e;
   const bf16* qkv;
@@ -268,7 +269,7 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const bool issuer = elect_one();
       int t = 0;
       for (int j = 0; j < my_items; ++j) {
-        const int item = blockIdx.x + j * gridDim.x;
+        const int item = p.reverse ? num_items - 1 - (int)(blockIdx.x + j * gridDim.x) : (int)(blockIdx.x + j * gridDim.x);
         const int seq = item >> 4, head = item & 15;
         const int r0 = 32 * (j & 3);
         mbar_wait(k_empty, (j & 1) ^ 1u, 21);
@@ -412,13 +413,13 @@ mha_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // the odd query row's element for thread tid2 < 64, fetched one item ahead (a global-load latency per item otherwise)
     auto load_q = [&](int jj) -> float {
       if (!stray_q || tid2 >= 64 || jj >= my_items) return 0.f;
-      const int it2 = blockIdx.x + jj * gridDim.x;
+      const int it2 = p.reverse ? num_items - 1 - (int)(blockIdx.x + jj * gridDim.x) : (int)(blockIdx.x + jj * gridDim.x);
       return __bfloat162float(p.qkv[((long long)(it2 >> 4) * p.seq_stride + NMAIN) * 3072 + (it2 & 15) * 64 + tid2]);
     };
     float q_next = load_q(0);
     int t = 0;
     for (int j = 0; j < my_items; ++j) {
-      const int item = blockIdx.x + j * gridDim.x;
+      const int item = p.reverse ? num_items - 1 - (int)(blockIdx.x + j * gridDim.x) : (int)(blockIdx.x + j * gridDim.x);
       const int seq = item >> 4, head = item & 15;
       const int r0 = 32 * (j & 3);
       if (stray_q) {
@@ -612,7 +613,7 @@ int sm_count() {
 }
 
 template <int NMAIN, bool STRAY>
-int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s) {
+int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s, bool reverse) {
   using C = Cfg<NMAIN, STRAY>;
   auto kern = mha_tc2_kernel<NMAIN, STRAY>;
   static bool configured = false;
@@ -629,6 +630,7 @@ int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_val
   if (int r = make_tmap_generic(&tst, 0, qkv, 3, dims, strides, 64, 16)) return r;
   AParams p{};
   p.nseq = nseq; p.seq_stride = seq_stride; p.seq_valid = seq_valid;
+  p.reverse = reverse ? 1 : 0;
   // 257 tokens (ViT): two full query tiles on the tensor cores, row 256 on the CUDA cores inside the softmax warps' idle windows
   static int stray_mode = -1;
   if (stray_mode < 0) { const char* e = getenv("AGB_ATTN_STRAY_TILE"); stray_mode = (e && e[0] == '1') ? 0 : 1; }   // A/B: 1 = third tile
@@ -667,9 +669,9 @@ int launch_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_val
 }  // namespace
 
 // returns -1 when the shape is not covered by an instantiation (caller falls back)
-int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s) {
-  if (seq_valid <= 112) return launch_tc2<112, false>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
-  if (seq_valid > 128 && seq_valid <= 257) return launch_tc2<256, true>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
+int attention_tc2(const bf16* qkv, bf16* out, int nseq, int seq_stride, int seq_valid, float scale, cudaStream_t s, bool reverse) {
+  if (seq_valid <= 112) return launch_tc2<112, false>(qkv, out, nseq, seq_stride, seq_valid, scale, s, reverse);
+  if (seq_valid > 128 && seq_valid <= 257) return launch_tc2<256, true>(qkv, out, nseq, seq_stride, seq_valid, scale, s, reverse);
   return -1;
 }
 

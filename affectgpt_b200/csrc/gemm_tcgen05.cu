@@ -82,6 +82,7 @@ struct KParams {
   int has_f32;            // fp32 output through tmF
   int reduce_f32;         // ... as an L2 reduce-add into the existing fp32 tensor (residual stream)
   int has_bf16;           // bf16 output through tmH
+  int reverse;            // tile schedule walks from the last tile to the first
 };
 
 template <int BN, int MODE, int ACT, int CG>
@@ -155,7 +156,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int sit = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step, ++sit) {
-        const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+        const int tl = p.reverse ? num_tiles - 1 - tile : tile;
+        const int mt = tl / p.n_tiles, nt = tl % p.n_tiles;
         const int row0 = mt * (BM * CG) + (int)cta_rank * BM;          // this CTA's 128 A rows
         const int wrow0 = nt * BN + (int)cta_rank * (BN / CG);          // this CTA's share of the W tile
         if constexpr (kSlab) {
@@ -284,7 +286,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     bool store_pending = false;
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const int tl = p.reverse ? num_tiles - 1 - tile : tile;
+      const int mt = tl / p.n_tiles, nt = tl % p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row_base = kPos ? q * 32 : mt * (BM * CG) + (int)cta_rank * BM + q * 32;
@@ -534,6 +537,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   kp.has_f32 = a.out_f32 != nullptr;
   kp.reduce_f32 = a.res != nullptr;
   kp.has_bf16 = a.out_bf16 != nullptr;
+  kp.reverse = a.reverse ? 1 : 0;
   if (a.out_f32) AGB_REQUIRE(a.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a.out_f32) & 15) == 0, "gemm: f32 out alignment");
   if (a.out_bf16) AGB_REQUIRE(a.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out_bf16) & 15) == 0, "gemm: bf16 out alignment");
   if (a.bias) AGB_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias alignment");

@@ -14,10 +14,11 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_f32_kernel(const float* __restrict__ x, long long ldx, long long rows,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     float eps, bf16* __restrict__ ob, long long ldb,
-                                                    float* __restrict__ of, long long ldf) {
+                                                    float* __restrict__ of, long long ldf, int reverse) {
   constexpr int D = NV * 128;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long r0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r0 >= rows) return;
+  const long long row = reverse ? rows - 1 - r0 : r0;       // last rows first: they are what the producer left in L2
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   float4 v[NV];
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(256) ln512_bf16_kernel(const bf16* x, long lon
 }  // namespace
 
 int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const float* gamma, const float* beta, float eps,
-                     bf16* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, cudaStream_t s) {
+                     bf16* out_bf16, int64_t ld_bf16, float* out_f32, int64_t ld_f32, cudaStream_t s, bool reverse) {
   AGB_REQUIRE(rows > 0, "layernorm: no rows");
   AGB_REQUIRE(D == 512 || D == 768 || D == 1024, "layernorm: D must be 512, 768 or 1024");
   AGB_REQUIRE(ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "layernorm: input alignment");
@@ -126,11 +127,11 @@ int layernorm_f32_in(const float* x, int64_t ldx, int64_t rows, int D, const flo
   LaunchTimer timer(PROF_LAYERNORM, 8.0 * rows * D, (double)rows * D * (4.0 + (out_bf16 ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)), s);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   if (D == 1024)
-    ln_f32_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
+    ln_f32_kernel<8><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32, reverse ? 1 : 0);
   else if (D == 768)
-    ln_f32_kernel<6><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
+    ln_f32_kernel<6><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32, reverse ? 1 : 0);
   else
-    ln_f32_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32);
+    ln_f32_kernel<4><<<grid, 256, 0, s>>>(x, ldx, rows, gamma, beta, eps, out_bf16, ld_bf16, out_f32, ld_f32, reverse ? 1 : 0);
   AGB_CHECK_LAUNCH();
   return 0;
 }
