@@ -195,6 +195,58 @@ def test_gpu_splice_raises_like_reference():
     assert torch.equal(out, emb)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["nq1", "nq_many", "other_order", "sample_without_placeholder", "frame_audio_only",
+                                  "err_count", "err_consecutive", "err_missing_face"])
+def test_gpu_splice_matches_reference_forward_fixture(name, dtype):
+    """reference_splice.npz: inputs_embeds produced by the reference's own AffectGPT.forward loop (affectgpt.py:956-1009,
+    tests/golden/make_reference_splice.py).  agb_splice_tokens reproduces it bit for bit and raises what it raises."""
+    from affectgpt_b200 import splice as P
+    from tests import splice_cases as SC
+    c = SC.stub_case(SC.fixture(), name)
+    emb = c["embeds"].to(dtype).to(DEV)
+    toks = {k: v.to(DEV) for k, v in c["tokens"].items()}
+    if c["error"] is not None:
+        exc = {"ValueError": ValueError, "AssertionError": AssertionError}[c["error"]["type"]]
+        with pytest.raises(exc) as e:
+            P.splice_tokens(emb, c["ids"].to(DEV), SC.TOK, c["nq"], toks)
+        assert str(e.value) == c["error"]["message"]
+        return
+    got = P.splice_tokens(emb, c["ids"].to(DEV), SC.TOK, c["nq"], toks)
+    assert got.dtype == dtype
+    assert torch.equal(got.float().cpu(), c["want"].to(dtype).float())
+
+
+def test_gpu_fused_tokens_spliced_like_reference_forward():
+    """'heads' case: reference encode_*_merge + its splice loop, end to end (pre-extracted features -> inputs_embeds).
+    Product: AffectGPTFusion heads (agb_*_fuse) + agb_splice_tokens.  Text rows bit-exact, fused rows to 1e-4."""
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import splice as P
+    from tests import splice_cases as SC
+    fix = SC.fixture()
+    ids = torch.from_numpy(fix["heads.ids"])
+    want = torch.from_numpy(fix["heads.inputs_embeds"])
+    emb = SC.embed_ids(ids, 3584, int(fix["heads.embed_seed"]))
+    frame_h, face_h, audio_h = (torch.from_numpy(fix[f"heads.{k}"]).to(DEV) for k in ("frame_h", "face_h", "audio_h"))
+    m = agb.AffectGPTFusion(None, None)
+    m.load_state_dict(R.build_fusion_state(seed=1234))
+    _, frame_llm = m.encode_video_merge(frame_h, None, is_preextracted=True)
+    face_hid, face_llm = m.encode_video_merge(face_h, None, is_preextracted=True)
+    audio_hid, audio_llm = m.encode_audio_merge(audio_h, None, is_preextracted=True)
+    _, multi_llm = m.encode_multi_merge(face_hid, audio_hid)
+    nq = {"frame": 1, "face": 1, "audio": 1, "multi": 1}
+    got = P.splice_tokens(emb.to(DEV), ids.to(DEV), SC.TOK, nq, {"frame": frame_llm, "face": face_llm, "audio": audio_llm,
+                                                                  "multi": multi_llm}).cpu()
+    ph = torch.zeros_like(ids, dtype=torch.bool)
+    for t in SC.TOK.values():
+        ph |= ids == t
+    assert int(ph.sum()) == 8
+    assert torch.equal(got[~ph], want[~ph])
+    err = float((got[ph] - want[ph]).abs().max()) / float(want[ph].abs().max())
+    print(f"[ref-golden] spliced fused tokens vs reference forward: rel err {err:.2e}")
+    assert err < 1e-4, err
+
+
 @pytest.mark.parametrize("orig,n,ch", [(44100, 97531, 1), (48000, 120000, 2), (22050, 30011, 1), (8000, 15999, 1), (11025, 40000, 2)])
 def test_gpu_resample_matches_torchaudio(orig, n, ch):
     """agb_resample_audio vs torchaudio.functional.resample (what load_audio calls, data.py:186-187): same filter bank,

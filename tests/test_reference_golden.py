@@ -126,3 +126,54 @@ def test_oracle_encoder_wrappers_match_reference_classes():
                        ("hubert3_layer_audio_seed5_b2_t2", R.synth_audio(2, 2, seed=5))):
         got = R.hubert_large_forward(hub, audio)
         assert float((got - torch.from_numpy(enc[key])).abs().max()) < 1e-4, key
+
+
+# ------------------------------------------------------------------------------------------------ token layout (a15)
+from affectgpt_b200 import splice as PS  # noqa: E402
+from tests import splice_cases as SC  # noqa: E402
+
+SPL = SC.fixture()
+
+
+@pytest.mark.parametrize("name", SC.STUB_CASES)
+def test_splice_oracle_and_host_positions_match_reference_forward(name):
+    """reference_splice.npz = inputs_embeds of the reference's own AffectGPT.forward (affectgpt.py:956-1009) run in the
+    build container; the oracle restatement reproduces it bit for bit and raises the same exceptions, and the host-side
+    position scan of the product agrees with where the reference put the tokens."""
+    c = SC.stub_case(SPL, name)
+    if c["error"] is not None:
+        exc = {"ValueError": ValueError, "AssertionError": AssertionError}[c["error"]["type"]]
+        with pytest.raises(exc) as e1:
+            OS.splice(c["embeds"], c["ids"], SC.TOK, c["nq"], c["tokens"])
+        assert str(e1.value) == c["error"]["message"]
+        with pytest.raises(exc) as e2:
+            PS.placeholder_positions(c["ids"], SC.TOK, c["nq"], list(c["tokens"]))
+        assert str(e2.value) == c["error"]["message"]
+        return
+    got = OS.splice(c["embeds"], c["ids"], SC.TOK, c["nq"], c["tokens"])
+    assert torch.equal(got, c["want"])
+    pos = PS.placeholder_positions(c["ids"], SC.TOK, c["nq"], list(c["tokens"]))
+    for k, starts in pos.items():
+        for i, s in enumerate(starts.tolist()):
+            if s >= 0:                                          # the reference's output carries the tokens exactly there
+                assert torch.equal(c["want"][i, s:s + c["nq"][k]], c["tokens"][k][i]), (name, k, i)
+
+
+def test_splice_after_reference_heads_end_to_end():
+    """'heads' case: the reference's real encode_*_merge (attention heads + projectors to 3584) in front of its loop.
+    Oracle heads + oracle splice vs that output: layout bit-exact (text rows equal), fused rows to 1e-5."""
+    st = R.build_fusion_state(seed=1234)
+    ids = torch.from_numpy(SPL["heads.ids"])
+    want = torch.from_numpy(SPL["heads.inputs_embeds"])
+    emb = SC.embed_ids(ids, 3584, int(SPL["heads.embed_seed"]))
+    frame_h, face_h, audio_h = (torch.from_numpy(SPL[f"heads.{k}"]) for k in ("frame_h", "face_h", "audio_h"))
+    toks = R.fused_tokens(st, frame_h, face_h, audio_h, "multiface_audio_face_frame_text")
+    nq = {"frame": 1, "face": 1, "audio": 1, "multi": 1}
+    got = OS.splice(emb, ids, SC.TOK, nq, toks)
+    placeholder = torch.zeros_like(ids, dtype=torch.bool)
+    for t in SC.TOK.values():
+        placeholder |= ids == t
+    assert int(placeholder.sum()) == 8
+    assert torch.equal(got[~placeholder], want[~placeholder])
+    err = float((got[placeholder] - want[placeholder]).abs().max()) / float(want[placeholder].abs().max())
+    assert err < 1e-5, err
