@@ -74,10 +74,14 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists():
+    from .build import build_lib, is_current
+    if not is_current():
+        # missing, or built from other sources than the ones on disk (a stale library would be used silently otherwise)
         if os.environ.get("AGB_AUTOBUILD", "1") == "1":
-            from .build import build_lib
-            build_lib()
+            build_lib()                                       # serialised across ranks by a file lock, atomic rename
+        elif _LIB_PATH.exists():
+            raise RuntimeError(f"{_LIB_PATH} is stale (csrc/ changed since it was built) and AGB_AUTOBUILD=0: "
+                               "rebuild with `python -m affectgpt_b200.build`")
         if not _LIB_PATH.exists():
             raise RuntimeError(
                 f"{_LIB_PATH} is missing: build it with `python -m affectgpt_b200.build` "

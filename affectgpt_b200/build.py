@@ -20,9 +20,17 @@ SOURCES = ["agb_api.cu", "gemm_tcgen05.cu", "layernorm.cu", "attention.cu", "att
            "fusion.cu", "qformer.cu", "staging.cu", "splice.cu", "pack.cu", "profile.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--use_fast_math", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     "-Xcompiler", "-Wall", "-Xptxas", "-v",
 ] + os.environ.get("AGB_NVCC_EXTRA", "").split()      # A/B experiments, e.g. AGB_NVCC_EXTRA=-DAGB_GELU_MUFU
+# --use_fast_math (approximate division / sqrt, FTZ) only where the arithmetic is bf16-tolerance work anyway.  The fp32
+# SIMT heads (fusion.cu, qformer.cu), the cv2-exact / torchaudio-exact staging kernels and the splice are compiled with
+# IEEE division and no FTZ: their results are held to 1e-4 .. bit-exact against the reference.
+PRECISE_SOURCES = {"fusion.cu", "qformer.cu", "staging.cu", "splice.cu", "pack.cu"}
+
+
+def flags_for(src: str):
+    return NVCC_FLAGS + ([] if src in PRECISE_SOURCES else ["--use_fast_math"])
 
 
 def _nvcc() -> str:
@@ -41,10 +49,34 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
+def is_current() -> bool:
+    """True when libagb.so exists and was built from the sources as they are now."""
+    try:
+        return LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == _fingerprint()
+    except OSError:
+        return False
+
+
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    fp = _fingerprint()
-    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
+    """Build (if stale) under an exclusive file lock: ranks of a torchrun job that import the package at the same time
+    serialise here, the first one builds, the others find a current library.  The link goes to a temporary file that is
+    renamed into place, so a concurrent dlopen never sees a truncated libagb.so."""
+    import fcntl
+    if not force and is_current():
         return LIB
+    (HERE / "build").mkdir(exist_ok=True)
+    with open(HERE / "build" / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
+    fp = _fingerprint()
     nvcc = _nvcc()
     objs = []
     build_dir = HERE / "build"
@@ -52,7 +84,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in SOURCES:
         obj = build_dir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *flags_for(src), "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False
@@ -68,12 +100,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed; see affectgpt_b200/build/nvcc.log")
     if verbose:
         print("\n".join(log))
-    link = [nvcc, "-shared", "-o", str(LIB), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    tmp = LIB.with_name(f".libagb.{os.getpid()}.so.tmp")
+    link = [nvcc, "-shared", "-o", str(tmp), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
             "-Xcompiler", "-fPIC"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
+        tmp.unlink(missing_ok=True)
         raise RuntimeError("link of libagb.so failed")
+    os.replace(tmp, LIB)
     STAMP.write_text(fp)
     return LIB
 

@@ -122,6 +122,13 @@ int dev_free(agb_ctx* c, void* p) {
   return 0;
 }
 
+// free + null: a failed re-allocation must never leave a dangling pointer behind a still-valid capacity
+template <typename T>
+void dev_release(agb_ctx* c, T*& p) {
+  dev_free(c, p);
+  p = nullptr;
+}
+
 void add_loader(agb_ctx* c, const std::string& name, std::vector<int64_t> shape,
                 std::function<int(const float*, cudaStream_t)> fn) {
   Loader l;
@@ -368,9 +375,10 @@ void tap(agb_ctx* c, const std::string& name, const void* src, int64_t bytes, cu
 // ------------------------------------------------------------------------------------ workspaces
 int ensure_vit_ws(agb_ctx* c, int64_t frames) {
   if (frames <= c->v_cap) return 0;
-  void* old[] = {c->v_apatch, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, c->v_clsln, c->v_patch_out, c->v_resid, c->v_qcls, c->v_acls};
-  for (void* p : old) dev_free(c, p);
   c->v_cap = 0;
+  dev_release(c, c->v_apatch); dev_release(c, c->v_xln); dev_release(c, c->v_qkv); dev_release(c, c->v_attn);
+  dev_release(c, c->v_h1); dev_release(c, c->v_clsln); dev_release(c, c->v_patch_out); dev_release(c, c->v_resid);
+  dev_release(c, c->v_qcls); dev_release(c, c->v_acls);
   const size_t M = (size_t)frames * 257;
   if (int r = dev_alloc(c, &c->v_apatch, (size_t)frames * 256 * 640)) return r;
   if (int r = dev_alloc(c, &c->v_patch_out, (size_t)frames * 256 * 1024)) return r;
@@ -388,9 +396,9 @@ int ensure_vit_ws(agb_ctx* c, int64_t frames) {
 
 int ensure_hub_ws(agb_ctx* c, int64_t segs) {
   if (segs <= c->h_cap) return 0;
-  void* old[] = {c->h_c0, c->h_c1, c->h_xln, c->h_qkv, c->h_attn, c->h_h1, c->h_resid, c->h_gn_acc};
-  for (void* p : old) dev_free(c, p);
   c->h_cap = 0;
+  dev_release(c, c->h_c0); dev_release(c, c->h_c1); dev_release(c, c->h_xln); dev_release(c, c->h_qkv);
+  dev_release(c, c->h_attn); dev_release(c, c->h_h1); dev_release(c, c->h_resid); dev_release(c, c->h_gn_acc);
   const size_t M = (size_t)segs * 100;
   if (int r = dev_alloc(c, &c->h_c0, (size_t)segs * 6400 * 512 + 4096)) return r;
   if (int r = dev_alloc(c, &c->h_c1, (size_t)segs * 3200 * 512 + 4096)) return r;
@@ -407,8 +415,9 @@ int ensure_hub_ws(agb_ctx* c, int64_t segs) {
 
 int ensure_stats(agb_ctx* c, int64_t groups) {
   if (groups <= c->h_stat_cap) return 0;
-  dev_free(c, c->h_stats);
-  dev_free(c, c->h_stat_acc);
+  c->h_stat_cap = 0;                      // capacities are set only after every allocation succeeded
+  dev_release(c, c->h_stats);
+  dev_release(c, c->h_stat_acc);
   if (int r = dev_alloc(c, &c->h_stats, (size_t)groups * 2)) return r;
   if (int r = dev_alloc(c, &c->h_stat_acc, (size_t)groups * 2)) return r;
   c->h_stat_cap = groups;
@@ -417,8 +426,8 @@ int ensure_stats(agb_ctx* c, int64_t groups) {
 
 int ensure_fuse_ws(agb_ctx* c, int64_t B) {
   if (B <= c->f_cap) return 0;
-  void* old[] = {c->f_a, c->f_b, c->f_c, c->f_d, c->f_e};
-  for (void* p : old) dev_free(c, p);
+  c->f_cap = 0;
+  dev_release(c, c->f_a); dev_release(c, c->f_b); dev_release(c, c->f_c); dev_release(c, c->f_d); dev_release(c, c->f_e);
   if (int r = dev_alloc(c, &c->f_a, (size_t)B * 1024)) return r;
   if (int r = dev_alloc(c, &c->f_b, (size_t)B * 1024)) return r;
   if (int r = dev_alloc(c, &c->f_c, (size_t)B * 2048)) return r;
@@ -658,10 +667,19 @@ int agb_load_tensor(agb_ctx* ctx, const char* name, const void* dev_ptr, int dty
   auto it = ctx->loaders.find(key);
   if (it == ctx->loaders.end()) { set_error("agb_load_tensor: unknown tensor name '" + key + "'"); return fail(ctx, 6); }
   if (dtype != AGB_DTYPE_F32) { set_error("agb_load_tensor: only fp32 source tensors are accepted"); return fail(ctx, 2); }
-  int64_t n = 1;
-  for (int i = 0; i < ndim; ++i) n *= shape[i];
-  if (n != numel(it->second.shape)) {
-    set_error("agb_load_tensor: element count mismatch for '" + key + "'");
+  // the full shape must match (leading / trailing singleton dimensions aside): an [in, out] tensor passed for an [out, in]
+  // weight has the right element count and would otherwise load silently
+  auto squeeze = [](const int64_t* d, int n) {
+    std::vector<int64_t> v;
+    for (int i = 0; i < n; ++i)
+      if (d[i] != 1) v.push_back(d[i]);
+    return v;
+  };
+  if (!shape || ndim <= 0 || squeeze(shape, ndim) != squeeze(it->second.shape.data(), (int)it->second.shape.size())) {
+    std::string want, got;
+    for (auto d : it->second.shape) want += (want.empty() ? "" : ",") + std::to_string(d);
+    for (int i = 0; shape && i < ndim; ++i) got += (got.empty() ? "" : ",") + std::to_string(shape[i]);
+    set_error("agb_load_tensor: shape mismatch for '" + key + "': expected [" + want + "], got [" + got + "]");
     return fail(ctx, 7);
   }
   if (int r = it->second.fn(static_cast<const float*>(dev_ptr), static_cast<cudaStream_t>(stream))) return fail(ctx, r);
@@ -813,8 +831,8 @@ namespace {
 int ensure_qf_ws(agb_ctx* c, int64_t q_rows, int64_t kv_rows, int64_t enc_elems) {
   QFormerWs& w = c->qf_ws;
   if (q_rows > w.cap_q) {
-    void* old[] = {w.x, w.t0, w.t1, w.t2, w.ff};
-    for (void* p : old) dev_free(c, p);
+    w.cap_q = 0;
+    dev_release(c, w.x); dev_release(c, w.t0); dev_release(c, w.t1); dev_release(c, w.t2); dev_release(c, w.ff);
     if (int r = dev_alloc(c, &w.x, (size_t)q_rows * 768)) return r;
     if (int r = dev_alloc(c, &w.t0, (size_t)q_rows * 768)) return r;
     if (int r = dev_alloc(c, &w.t1, (size_t)q_rows * 768)) return r;
@@ -823,13 +841,15 @@ int ensure_qf_ws(agb_ctx* c, int64_t q_rows, int64_t kv_rows, int64_t enc_elems)
     w.cap_q = q_rows;
   }
   if (kv_rows > w.cap_kv) {
-    dev_free(c, w.kx); dev_free(c, w.vx);
+    w.cap_kv = 0;
+    dev_release(c, w.kx); dev_release(c, w.vx);
     if (int r = dev_alloc(c, &w.kx, (size_t)kv_rows * 768)) return r;
     if (int r = dev_alloc(c, &w.vx, (size_t)kv_rows * 768)) return r;
     w.cap_kv = kv_rows;
   }
   if (enc_elems > w.cap_enc) {
-    dev_free(c, w.enc); dev_free(c, w.ev); dev_free(c, w.ea);
+    w.cap_enc = 0;
+    dev_release(c, w.enc); dev_release(c, w.ev); dev_release(c, w.ea);
     if (int r = dev_alloc(c, &w.enc, (size_t)enc_elems)) return r;
     if (int r = dev_alloc(c, &w.ev, (size_t)enc_elems)) return r;
     if (int r = dev_alloc(c, &w.ea, (size_t)enc_elems)) return r;

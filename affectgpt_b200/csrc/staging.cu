@@ -42,10 +42,20 @@ __device__ __forceinline__ Tap cv_linear_tap(int d, int src, int dst, bool reset
 }
 
 // grid (224 rows, T frames), block 224: out[t, c, dy, dx] <- faces[idx[t]] resized
-__global__ void __launch_bounds__(224) face_resize_kernel(const uint8_t* __restrict__ faces, int h, int w,
-                                                         const int* __restrict__ idx, uint8_t* __restrict__ out) {
+// A crop index outside [0, n_src) is a caller error the C ABI cannot see before the launch (the indices live in device
+// memory): such a frame is written as zeros and flagged in *bad (checked by agb_stage_faces after the launch).
+__global__ void __launch_bounds__(224) face_resize_kernel(const uint8_t* __restrict__ faces, int n_src, int h, int w,
+                                                         const int* __restrict__ idx, uint8_t* __restrict__ out,
+                                                         int* __restrict__ bad) {
   const int dy = blockIdx.x, t = blockIdx.y, dx = threadIdx.x;
-  const uint8_t* img = faces + (long long)idx[t] * h * w * 3;
+  const int src = idx[t];
+  if (src < 0 || src >= n_src) {
+    if (dy == 0 && dx == 0) atomicAdd(bad, 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(((long long)t * 3 + c) * 224 + dy) * 224 + dx] = 0;
+    return;
+  }
+  const uint8_t* img = faces + (long long)src * h * w * 3;
   const Tap ty = cv_linear_tap(dy, h, 224, false);
   const Tap tx = cv_linear_tap(dx, w, 224, true);
   const uint8_t* r0 = img + (long long)ty.i0 * w * 3;
@@ -113,16 +123,29 @@ int resample_f32(const float* wav, int ch, int64_t n, const float* bank, int ori
 
 int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int* idx_dev, int T, uint8_t* out,
                    cudaStream_t s) {
-  AGB_REQUIRE(faces && idx_dev && out && n_src > 0 && h > 0 && w > 0 && T > 0, "stage_faces: bad arguments");
-  LaunchTimer timer(PROF_FRONTEND, 0.0, (double)T * (4.0 * 3 * 224 * 224 + 3.0 * 224 * 224), s);
-  face_resize_kernel<<<dim3(224, T), 224, 0, s>>>(faces, h, w, idx_dev, out);
-  AGB_CHECK_LAUNCH();
+  AGB_REQUIRE(faces && idx_dev && out && n_src > 0 && n_src < (1ll << 31) && h > 0 && w > 0 && T > 0,
+              "stage_faces: bad arguments");
+  static int* bad_dev = nullptr;            // one 4-byte counter per process (staging is not on the graph-captured path)
+  if (bad_dev == nullptr) AGB_CHECK_CUDA(cudaMalloc(&bad_dev, sizeof(int)));
+  AGB_CHECK_CUDA(cudaMemsetAsync(bad_dev, 0, sizeof(int), s));
+  {
+    LaunchTimer timer(PROF_FRONTEND, 0.0, (double)T * (4.0 * 3 * 224 * 224 + 3.0 * 224 * 224), s);
+    face_resize_kernel<<<dim3(224, T), 224, 0, s>>>(faces, (int)n_src, h, w, idx_dev, out, bad_dev);
+    AGB_CHECK_LAUNCH();
+  }
+  int bad = 0;
+  AGB_CHECK_CUDA(cudaMemcpyAsync(&bad, bad_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  AGB_CHECK_CUDA(cudaStreamSynchronize(s));
+  AGB_REQUIRE(bad == 0, "stage_faces: a crop index lies outside [0, n_src)");
   return 0;
 }
 
 int stage_audio_f32(const float* wav, int ch, int64_t n, const long long* starts_dev, int clips, int clip_len, float* out,
                     cudaStream_t s) {
   AGB_REQUIRE(wav && starts_dev && out && ch >= 1 && n >= 0 && clips > 0 && clip_len > 0, "stage_audio: bad arguments");
+  // load_audio averages exactly two channels and keeps any other channel count as it is (data.py:190-191); the
+  // [clips, 1, clip_len] output of this entry point can only represent the mono and the stereo case
+  AGB_REQUIRE(ch <= 2, "stage_audio: more than two channels are not supported (mix down on the caller side)");
   LaunchTimer timer(PROF_FRONTEND, 0.0, (double)clips * clip_len * 4.0 * (ch == 2 ? 3.0 : 2.0), s);
   audio_gather_kernel<<<dim3(32, clips), 256, 0, s>>>(wav, ch, n, starts_dev, clip_len, out);
   AGB_CHECK_LAUNCH();

@@ -57,13 +57,21 @@ def _au_info(video_name: Optional[str], mer_factory_output: Optional[str]) -> Op
 
 def frame_indices(vlen: int, n_frms: int, sampling_mode: str, video_name: Optional[str] = None,
                   mer_factory_output: Optional[str] = None) -> List[int]:
-    """The index rule of load_video (video_processor.py:204-244)."""
+    """The index rule of the extractor's extract_frame_features (A/extract_multimodal_features_precompute.py:160-176).
+
+    uniform / headtail go through load_video (video_processor.py:204-244).  ``emotion_peak`` with a video name does NOT:
+    the extractor branches to extract_frame_features_smart (:174-175, :231-258), i.e. calculate_smart_frame_indices
+    (:389-526) on the clip's au_info - always 8 frames, and ``np.linspace(0, vlen - 1, 8)`` when the AU json is missing,
+    has no au_info or no peak_frames (:400-403).  Only without a video name does it fall through to load_video, whose
+    emotion_peak rule without au_info repeats the middle frame (video_processor.py:229-237)."""
     if sampling_mode == "uniform":
         return sampling.uniform_frame_indices(vlen, n_frms)
     if sampling_mode == "headtail":
         return sampling.headtail_frame_indices(vlen, n_frms)
     if sampling_mode == "emotion_peak":
-        return sampling.emotion_peak_frame_indices(vlen, _au_info(video_name, mer_factory_output), n_frms)
+        if video_name:
+            return sampling.smart_frame_indices(_au_info(video_name, mer_factory_output), vlen)
+        return sampling.emotion_peak_frame_indices(vlen, None, n_frms)
     raise NotImplementedError(sampling_mode)
 
 

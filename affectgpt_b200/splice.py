@@ -66,7 +66,13 @@ def splice_tokens(input_embeds: torch.Tensor, input_ids: torch.Tensor, token_ids
     names = [n for n in ORDER if n in token_ids]
     if not names:
         return input_embeds if inplace else input_embeds.clone()
-    out = input_embeds if (inplace and input_embeds.is_contiguous()) else input_embeds.contiguous().clone()
+    if inplace and input_embeds.is_contiguous():
+        # in place there is no copy to fall back on: validate every sample first (same exceptions, same order), so that a
+        # ValueError / AssertionError never leaves a half-spliced tensor behind
+        placeholder_positions(ids, token_ids, n_query, [n for n in names if embeds.get(n) is not None])
+        out = input_embeds
+    else:
+        out = input_embeds.contiguous().clone()
     keep = []                                                   # staging tensors must outlive the launch
     tok = (C.c_int64 * len(names))(*[int(token_ids[n]) for n in names])
     nq = (C.c_int32 * len(names))(*[int(n_query.get(n, 0)) for n in names])

@@ -2,7 +2,7 @@
 
 Reference: ``load_face`` (A/my_affectgpt/processors/video_processor.py:262-296) and ``load_audio``
 (A/my_affectgpt/models/ImageBind/data.py:170-214).  Decoding (np.load / torchaudio / decord) stays with the caller; what
-X
+runs here, as CUDA kernels behind the C ABI, is everything after it: the bilinear resize of the SAMPLED face crops only
 (the reference resizes every crop on the CPU and then samples 8), the mono mix-down, the 2-second zero padding and the
 eight-slice gather.  Index rules run on the host and are bit-exact (``sampling``).  No CPU fallback.
 """

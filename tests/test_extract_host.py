@@ -115,7 +115,21 @@ def test_csv_sample_source_and_frame_index_rules(tmp_path):
     args = X.build_parser().parse_args(["--dataset", "meld", "--csv_path", str(csv)])
     assert X.read_sample_names(args) == ["clip_a", "clip_b"]
     assert X.frame_indices(88, 8, "uniform") == [0, 11, 22, 33, 44, 55, 66, 77]
-    assert X.frame_indices(88, 8, "emotion_peak") == [44] * 8
+    assert X.frame_indices(88, 8, "emotion_peak") == [44] * 8          # no video name: load_video's rule (:229-237)
+    # with a video name the extractor takes extract_frame_features_smart (extract_...precompute.py:174-175): a missing
+    # *_au_analysis.json means np.linspace(0, vlen - 1, 8), never the repeated middle frame (:400-403)
+    import numpy as np
+    want = sorted(np.linspace(0, 87, 8).astype(int).tolist())
+    assert X.frame_indices(88, 8, "emotion_peak", "clip_a", str(tmp_path)) == want
+    assert X.frame_indices(88, 8, "emotion_peak", "clip_a", None) == want
+    d = tmp_path / "clip_b"
+    d.mkdir()
+    (d / "clip_b_au_analysis.json").write_text('{"au_info": {"total_frames": 88, "peak_frames": []}}')   # no peaks: same fallback
+    assert X.frame_indices(88, 8, "emotion_peak", "clip_b", str(tmp_path)) == want
+    (d / "clip_b_au_analysis.json").write_text(
+        '{"au_info": {"total_frames": 88, "peak_frames": [{"peak_index": 40, "frames_before_peak": 3, "frames_after_peak": 3}]}}')
+    got = X.frame_indices(88, 8, "emotion_peak", "clip_b", str(tmp_path))
+    assert len(got) == 8 and {38, 39, 40, 41, 42} <= set(got) and got == sorted(got)
     assert X.frame_indices(5, 8, "uniform") == [0, 1, 2, 3, 4, 4, 4, 4]
 
 
