@@ -1,13 +1,16 @@
 """Data-parallel sharding of clips across ranks (one process + one engine replica per GPU).
 
 Clips are independent: rank r takes clips r, r+W, r+2W, ...; there is no data-path collective.
-The only exchange step is the optional gather of fused tokens to the ranks that consume them
-(``gather_clip_rows``: one all_gather over NCCL/NVLink, or gloo in CPU tests).  The reference has no analogue
-for extraction (single GPU); its training uses DistributedSampler (A/my_affectgpt/runners/runner_base.py:548).
+The only exchange step is the optional gather of fused tokens to the ranks that consume them: one
+``all_gather_into_tensor`` over NCCL/NVLink (gloo in the CPU tests) into pre-allocated buffers, followed by ONE strided
+copy that puts the rows back in clip order.  ``ClipGather`` issues both on a side stream: the collective of step i
+overlaps the encoders of step i+1 and never paces the compute stream (a blocking rendez-vous on the compute stream
+makes every step wait for the slowest power-capped GPU of the node).  The reference has no analogue for extraction
+(single GPU); its training uses DistributedSampler (A/my_affectgpt/runners/runner_base.py:548).
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -24,9 +27,83 @@ def shard_sizes(num_clips: int, world_size: int) -> List[int]:
     return [len(range(r, num_clips, world_size)) for r in range(world_size)]
 
 
-def gather_clip_rows(local_rows: torch.Tensor, num_clips: int, group=None) -> torch.Tensor:
+def _all_gather_flat(recv: torch.Tensor, send: torch.Tensor, group) -> None:
+    """recv [W * n] <- every rank's send [n] (rank-major)."""
+    dist.all_gather_into_tensor(recv, send, group=group)
+
+
+class ClipGather:
+    """Gather of per-clip rows for one fixed shape: buffers allocated once, collective + reorder on a side stream.
+
+        g = ClipGather(num_clips, row_shape, dtype, device)
+        g.start(local_rows)          # returns immediately; the calling stream is not blocked
+        ... next step's kernels ...
+        rows = g.wait()              # [num_clips, *row_shape] in clip order; the calling stream now waits for the gather
+
+    ``start`` snapshots ``local_rows`` (device-to-device copy on the side stream after the producing work on the calling
+    stream), so the caller may overwrite them with the next step.  A second ``start`` before ``wait`` queues behind the
+    first one on the side stream and reuses the buffers: ``wait`` then returns the latest result.  On CPU tensors (gloo)
+    everything runs synchronously."""
+
+    def __init__(self, num_clips: int, row_shape: Sequence[int], dtype: torch.dtype, device, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("ClipGather needs an initialised process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.num_clips = int(num_clips)
+        self.sizes = shard_sizes(self.num_clips, self.world)
+        self.pad = max(self.sizes) if self.sizes else 0
+        self.row_shape = tuple(int(d) for d in row_shape)
+        dev = torch.device(device)
+        self.device = dev
+        self.send = torch.zeros((self.pad,) + self.row_shape, dtype=dtype, device=dev)       # rows >= my shard stay zero
+        self.recv = torch.empty((self.world, self.pad) + self.row_shape, dtype=dtype, device=dev)
+        # clip i = j * W + r sits at recv[r, j]: viewed as [pad, W, ...] the output is one strided copy of recv^T;
+        # the padding rows of uneven shards all land behind row num_clips
+        self.out_padded = torch.empty((self.pad * self.world,) + self.row_shape, dtype=dtype, device=dev)
+        self.cuda = dev.type == "cuda"
+        if self.cuda:
+            self.stream = torch.cuda.Stream(device=dev)
+            self.ready = torch.cuda.Event()
+            self.done = torch.cuda.Event()
+        self._pending = False
+
+    def start(self, local_rows: torch.Tensor) -> None:
+        n = self.sizes[self.rank]
+        if tuple(local_rows.shape) != (n,) + self.row_shape:
+            raise ValueError(f"rank {self.rank} holds rows of shape {tuple(local_rows.shape)}, expected {(n,) + self.row_shape}")
+        if not self.cuda:
+            self._run(local_rows)
+            self._pending = True
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.ready.record(cur)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ready)
+            local_rows.record_stream(self.stream)
+            self._run(local_rows)
+            self.done.record(self.stream)
+        self._pending = True
+
+    def _run(self, local_rows: torch.Tensor) -> None:
+        self.send[: self.sizes[self.rank]].copy_(local_rows, non_blocking=True)
+        _all_gather_flat(self.recv.view(-1), self.send.view(-1), self.group)
+        self.out_padded.view((self.pad, self.world) + self.row_shape).copy_(self.recv.transpose(0, 1), non_blocking=True)
+
+    def wait(self) -> torch.Tensor:
+        if not self._pending:
+            raise RuntimeError("ClipGather.wait() without a start()")
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_event(self.done)
+        return self.out_padded[: self.num_clips]
+
+
+def gather_clip_rows(local_rows: torch.Tensor, num_clips: int, group=None,
+                     gatherer: Optional[ClipGather] = None) -> torch.Tensor:
     """local_rows [n_local, ...] for this rank's strided shard -> [num_clips, ...] on every rank, rows back in
-    clip order.  Uneven shards are padded to the largest shard for the collective and trimmed after."""
+    clip order (blocking convenience form of ``ClipGather``: start + wait).  Uneven shards are padded to the largest
+    shard for the collective and trimmed after.  Pass a ``gatherer`` to reuse its buffers across calls."""
     if not dist.is_available() or not dist.is_initialized():
         if local_rows.shape[0] != num_clips:
             raise ValueError("without a process group the local shard must be the whole batch")
@@ -36,12 +113,7 @@ def gather_clip_rows(local_rows: torch.Tensor, num_clips: int, group=None) -> to
     sizes = shard_sizes(num_clips, world)
     if local_rows.shape[0] != sizes[rank]:
         raise ValueError(f"rank {rank} holds {local_rows.shape[0]} rows, expected {sizes[rank]}")
-    pad = max(sizes)
-    buf = local_rows.new_zeros((pad,) + tuple(local_rows.shape[1:]))
-    buf[: sizes[rank]] = local_rows
-    gathered = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(gathered, buf.contiguous(), group=group)
-    out = local_rows.new_empty((num_clips,) + tuple(local_rows.shape[1:]))
-    for r in range(world):
-        out[r::world] = gathered[r][: sizes[r]]
-    return out
+    if gatherer is None:
+        gatherer = ClipGather(num_clips, local_rows.shape[1:], local_rows.dtype, local_rows.device, group)
+    gatherer.start(local_rows.contiguous())
+    return gatherer.wait()

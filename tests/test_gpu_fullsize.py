@@ -112,3 +112,92 @@ def test_graphed_step_is_bit_identical_and_reusable(full_path):
         want, _ = _tokens(full_path, frames, audio)
         got = torch.cat([out["multi"], out["audio"], out["frame"]], dim=1)
         assert torch.equal(got, want), seed
+
+
+# ------------------------------------------------------------------------------------------------ oracle anchors at depth
+@pytest.fixture(scope="module")
+def oracle_models():
+    """The fp32 oracle (HF modules) loaded with the same synthetic 24-layer checkpoints as ``full_path``."""
+    from affectgpt_b200 import synthetic as S
+    clip = R.build_clip_vision(24, seed=1)
+    clip.load_state_dict({k: v.cpu() for k, v in S.clip_state(24, DEV).items()}, strict=False)
+    hub = R.build_hubert(24, "layer", seed=1)
+    missing, unexpected = hub.load_state_dict({k: v.cpu() for k, v in S.hubert_state(24, "layer", DEV).items()}, strict=False)
+    assert not unexpected and all("masked_spec_embed" in k for k in missing), (missing, unexpected)
+    fus = {k: v.cpu() for k, v in S.fusion_state(3584, DEV).items()}
+    return clip, hub, fus
+
+
+def test_c4_clip_against_oracle(full_path, oracle_models):
+    """One C4-shaped clip - 16 frames + 16 face crops + 16 x 2 s of audio, three-stream pre-fusion - through the fp32
+    oracle on identical weights (BASELINE gate on every token and on the per-modality hiddens)."""
+    from affectgpt_b200 import synthetic as S
+    clip, hub, fus = oracle_models
+    frames, faces, audio = S.frames(1, 16, seed=71), S.frames(1, 16, seed=72), S.audio(1, 16, seed=73)
+    toks, out = _tokens(full_path, frames.to(DEV), audio.to(DEV), faces.to(DEV))
+    fh, ch, ah = R.clip_vit_large_forward(clip, frames), R.clip_vit_large_forward(clip, faces), R.hubert_large_forward(hub, audio)
+    gate(out["frame_hiddens"], fh, "C4 frame hiddens [1,16,768]")
+    gate(out["face_hiddens"], ch, "C4 face hiddens [1,16,768]")
+    gate(out["audio_hiddens"], ah, "C4 audio hiddens [1,16,1024]")
+    want = R.fused_tokens(fus, fh, ch, ah, "multiface_audio_face_frame_text")
+    ref = torch.cat([want["multi"], want["audio"], want["face"], want["frame"]], dim=1)
+    gate(toks.reshape(4, 3584), ref.reshape(4, 3584), "C4 clip tokens <Multi><Audio><Face><Frame>")
+    assert R.nn_identity(out["frame_hiddens"][0].cpu(), fh[0]) and R.nn_identity(out["audio_hiddens"][0].cpu(), ah[0])
+
+
+def test_hubert_group_norm_at_24_layers_against_oracle():
+    """feat_extract_norm='group' (GroupNorm(512, 512) after conv0 only, base-family front-end) under the full 24-layer
+    encoder: one clip of 8 segments vs HF HubertModel with that config."""
+    import affectgpt_b200 as agb
+    hub = R.build_hubert(num_layers=24, feat_extract_norm="group", seed=4321)
+    eng = agb.Engine(DEV, vit_layers=2, hubert_layers=24, feat_extract_norm="group")
+    enc = agb.HUBERT_LARGE(model_dir="", num_layers=24, feat_extract_norm="group")
+    enc.load_hf_state_dict(hub.state_dict())
+    enc.attach_engine(eng)
+    raw = R.synth_audio(1, 8, seed=81)
+    got = enc(None, raw.to(DEV))
+    want = R.hubert_large_forward(hub, raw)
+    gate(got, want, "hubert24[group] features [1,8,1024]")
+    assert R.nn_identity(got[0].cpu(), want[0])
+    eng.close()
+
+
+@pytest.mark.parametrize("scale", [60.0, 100.0])
+def test_outlier_channels_in_the_residual_stream(scale):
+    """Trained CLIP-L / HuBERT carry 'massive activation' channels in the residual stream (a handful of channels 50-100x
+    the others) that random init never produces.  Inject them: a few output-bias entries of an early MLP are set to
+    +-scale, so every later block sees a residual row whose variance is dominated by 3-5 channels.  Same gate as
+    everywhere else, on 8-layer encoders (the oracle stays in seconds), plus the per-block taps after the injection."""
+    import affectgpt_b200 as agb
+    clip = R.build_clip_vision(num_layers=8, seed=77)
+    hub = R.build_hubert(num_layers=8, feat_extract_norm="layer", seed=77)
+    chans = [7, 300, 511, 901, 1023]
+    with torch.no_grad():
+        for i, c in enumerate(chans):
+            sign = 1.0 if i % 2 == 0 else -1.0
+            clip.vision_model.encoder.layers[1].mlp.fc2.bias[c] = sign * scale * (0.6 + 0.1 * i)
+            hub.encoder.layers[1].feed_forward.output_dense.bias[c] = -sign * scale * (0.6 + 0.1 * i)
+    fus = R.build_fusion_state(seed=1234)
+    model = agb.build_path(clip.state_dict(), hub.state_dict(), fus, device=DEV, vit_layers=8, hubert_layers=8)
+    eng = model._engine
+    raw = R.synth_frames(1, 2, seed=91)
+    vt = {n: eng.tap(n, (2 * 257, 1024)) for n in ("vit.block1", "vit.block4")}
+    got = model.visual_encoder(None, raw.to(DEV))
+    eng.clear_taps()
+    px = R.clip_preprocess(raw)
+    with torch.no_grad():
+        hs = clip.vision_model(pixel_values=px, output_hidden_states=True).hidden_states
+    assert float(hs[2].abs().max()) > 0.5 * scale                                  # the outliers are really there
+    gate(vt["vit.block1"].reshape(2, 257, 1024), hs[2], f"outlier x{scale:g}: vit.block1")
+    gate(vt["vit.block4"].reshape(2, 257, 1024), hs[5], f"outlier x{scale:g}: vit.block4")
+    gate(got, R.clip_vit_large_forward(clip, raw), f"outlier x{scale:g}: clip features")
+    audio = R.synth_audio(1, 2, seed=92)
+    at = {n: eng.tap(n, (2 * 100, 1024)) for n in ("hubert.block1", "hubert.block4")}
+    got_a = model.acoustic_encoder(None, audio.to(DEV))
+    eng.clear_taps()
+    want_a, ahs = R.hubert_large_forward(hub, audio, return_hidden_states=True)
+    assert float(ahs[2].abs().max()) > 0.5 * scale
+    gate(at["hubert.block1"].reshape(2, 100, 1024)[:, :99], ahs[2], f"outlier x{scale:g}: hubert.block1")
+    gate(at["hubert.block4"].reshape(2, 100, 1024)[:, :99], ahs[5], f"outlier x{scale:g}: hubert.block4")
+    gate(got_a, want_a, f"outlier x{scale:g}: hubert features")
+    eng.close()

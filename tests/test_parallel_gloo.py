@@ -34,7 +34,13 @@ def _worker(rank, world, port, num_clips, q):
         full = torch.arange(num_clips * 4 * 6, dtype=torch.float32).reshape(num_clips, 4, 6)   # [clips, tokens, D]
         mine = full[P.shard_indices(num_clips, rank, world)]
         got = P.gather_clip_rows(mine, num_clips)
-        q.put((rank, bool(torch.equal(got, full))))
+        ok = bool(torch.equal(got, full))
+        # the pre-allocated form, reused across steps (what bench.py / a consumer loop does)
+        g = P.ClipGather(num_clips, (4, 6), torch.float32, "cpu")
+        for step in range(3):
+            g.start(mine + step)
+            ok = ok and bool(torch.equal(g.wait(), full + step))
+        q.put((rank, ok))
     finally:
         dist.destroy_process_group()
 
