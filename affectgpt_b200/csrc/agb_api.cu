@@ -76,6 +76,7 @@ struct agb_ctx {
   bf16 *v_apatch = nullptr, *v_xln = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_h1 = nullptr, *v_clsln = nullptr;
   bf16 *v_qcls = nullptr, *v_acls = nullptr;   // pruned last block: CLS queries / CLS attention output [frames,1024]
   float *v_patch_out = nullptr, *v_resid = nullptr;
+  int *v_lncnt = nullptr, *h_lncnt = nullptr;   // per-256-row-block arrival counters of the fused LayerNorm (zero at rest)
   int64_t h_cap = 0;  // segments
   bf16 *h_c0 = nullptr, *h_c1 = nullptr, *h_xln = nullptr, *h_qkv = nullptr, *h_attn = nullptr, *h_h1 = nullptr;
   float *h_resid = nullptr, *h_stats = nullptr;
@@ -378,7 +379,7 @@ int ensure_vit_ws(agb_ctx* c, int64_t frames) {
   c->v_cap = 0;
   dev_release(c, c->v_apatch); dev_release(c, c->v_xln); dev_release(c, c->v_qkv); dev_release(c, c->v_attn);
   dev_release(c, c->v_h1); dev_release(c, c->v_clsln); dev_release(c, c->v_patch_out); dev_release(c, c->v_resid);
-  dev_release(c, c->v_qcls); dev_release(c, c->v_acls);
+  dev_release(c, c->v_qcls); dev_release(c, c->v_acls); dev_release(c, c->v_lncnt);
   const size_t M = (size_t)frames * 257;
   if (int r = dev_alloc(c, &c->v_apatch, (size_t)frames * 256 * 640)) return r;
   if (int r = dev_alloc(c, &c->v_patch_out, (size_t)frames * 256 * 1024)) return r;
@@ -390,6 +391,7 @@ int ensure_vit_ws(agb_ctx* c, int64_t frames) {
   if (int r = dev_alloc(c, &c->v_clsln, (size_t)frames * 1024)) return r;
   if (int r = dev_alloc(c, &c->v_qcls, (size_t)frames * 1024)) return r;
   if (int r = dev_alloc(c, &c->v_acls, (size_t)frames * 1024)) return r;
+  if (int r = dev_alloc(c, &c->v_lncnt, M / 256 + 2)) return r;
   c->v_cap = frames;
   return 0;
 }
@@ -399,6 +401,7 @@ int ensure_hub_ws(agb_ctx* c, int64_t segs) {
   c->h_cap = 0;
   dev_release(c, c->h_c0); dev_release(c, c->h_c1); dev_release(c, c->h_xln); dev_release(c, c->h_qkv);
   dev_release(c, c->h_attn); dev_release(c, c->h_h1); dev_release(c, c->h_resid); dev_release(c, c->h_gn_acc);
+  dev_release(c, c->h_lncnt);
   const size_t M = (size_t)segs * 100;
   if (int r = dev_alloc(c, &c->h_c0, (size_t)segs * 6400 * 512 + 4096)) return r;
   if (int r = dev_alloc(c, &c->h_c1, (size_t)segs * 3200 * 512 + 4096)) return r;
@@ -409,6 +412,7 @@ int ensure_hub_ws(agb_ctx* c, int64_t segs) {
   if (int r = dev_alloc(c, &c->h_h1, M * 4096)) return r;
   // group variant: per-(segment, channel) fp64 sum / sumsq; layer variant: the 32 KB packed conv0 filter matrix
   if (int r = dev_alloc(c, &c->h_gn_acc, c->cfg.hubert_conv_norm == 1 ? (size_t)segs * 1024 : (size_t)4096)) return r;
+  if (int r = dev_alloc(c, &c->h_lncnt, M / 256 + 2)) return r;
   c->h_cap = segs;
   return 0;
 }
@@ -449,11 +453,14 @@ bool zigzag_on() {
   return v == 1;
 }
 
-int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* attn, bf16* h1, int64_t M, int nseq,
-                  int seq_stride, int seq_valid, int act, cudaStream_t s, bool& flip) {
+// On entry xln holds LayerNorm_A(resid) (written by the previous block's FC2, or by the caller for the first block).  The
+// two residual GEMMs emit the LayerNorm that follows them (out-proj -> this block's LN_B; FC2 -> the NEXT block's LN_A when
+// `next` is given), fused into the GEMM's tail where the shape allows (gemm_tcgen05.cu, "LNF"): per block the chain is
+// QKV -> MHA -> out-proj(+LN) -> FC1 -> FC2(+LN), five kernels, no stand-alone LayerNorm pass.
+int encoder_block(const EncLayerW& L, const EncLayerW* next, float* resid, bf16* xln, bf16* qkv, bf16* attn, bf16* h1, int* lncnt,
+                  int64_t M, int nseq, int seq_stride, int seq_valid, int act, cudaStream_t s, bool& flip) {
   const bool zz = zigzag_on();
   auto dir = [&]() { const bool r = zz && flip; flip = !flip; return r; };
-  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnA_g, L.lnA_b, 1e-5f, xln, 1024, nullptr, 0, s, dir())) return r;
   GemmArgs g;
   g.A = xln; g.lda = 1024; g.W = L.wqkv; g.M = (int)M; g.N = 3072; g.K = 1024; g.bias = L.bqkv;
   g.out_bf16 = qkv; g.ld_bf16 = 3072; g.reverse = dir();
@@ -462,8 +469,8 @@ int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* 
   g = GemmArgs();
   g.A = attn; g.lda = 1024; g.W = L.wo; g.M = (int)M; g.N = 1024; g.K = 1024; g.bias = L.bo;
   g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024; g.reverse = dir();
+  g.ln_out = xln; g.ln_gamma = L.lnB_g; g.ln_beta = L.lnB_b; g.ln_eps = 1e-5f; g.ln_counters = lncnt;
   if (int r = gemm_bf16(g, s)) return r;
-  if (int r = layernorm_f32_in(resid, 1024, M, 1024, L.lnB_g, L.lnB_b, 1e-5f, xln, 1024, nullptr, 0, s, dir())) return r;
   g = GemmArgs();
   g.A = xln; g.lda = 1024; g.W = L.w1; g.M = (int)M; g.N = 4096; g.K = 1024; g.bias = L.b1; g.act = act;
   g.out_bf16 = h1; g.ld_bf16 = 4096; g.reverse = dir();
@@ -471,6 +478,9 @@ int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* 
   g = GemmArgs();
   g.A = h1; g.lda = 4096; g.W = L.w2; g.M = (int)M; g.N = 1024; g.K = 4096; g.bias = L.b2;
   g.res = resid; g.ld_res = 1024; g.out_f32 = resid; g.ld_f32 = 1024; g.reverse = dir();
+  if (next != nullptr) {
+    g.ln_out = xln; g.ln_gamma = next->lnA_g; g.ln_beta = next->lnA_b; g.ln_eps = 1e-5f; g.ln_counters = lncnt;
+  }
   return gemm_bf16(g, s);
 }
 
@@ -480,7 +490,7 @@ int encoder_block(const EncLayerW& L, float* resid, bf16* xln, bf16* qkv, bf16* 
 // row as the dense block; 5.66 of the block's 6.75 GFLOP per frame are not executed.
 int vit_last_block_cls(agb_ctx* c, const EncLayerW& L, int64_t F, cudaStream_t s) {
   const int64_t M = F * 257, pitch = 257 * 1024;
-  if (int r = layernorm_f32_in(c->v_resid, 1024, M, 1024, L.lnA_g, L.lnA_b, 1e-5f, c->v_xln, 1024, nullptr, 0, s)) return r;
+  // v_xln already holds LayerNorm_1(resid): written by the previous block's FC2 (or by clip_chunk for a 1-layer tower)
   GemmArgs g;
   g.A = c->v_xln; g.lda = 1024; g.W = L.wqkv + 1024ull * 1024; g.M = (int)M; g.N = 2048; g.K = 1024; g.bias = L.bqkv + 1024;
   g.out_bf16 = c->v_qkv + 1024; g.ld_bf16 = 3072;
@@ -518,13 +528,20 @@ int clip_chunk(agb_ctx* c, const void* frames, int in_dtype, int64_t F, float* o
   const int last = c->cfg.vit_layers - 1;
   const bool dense_last = c->cfg.vit_dense_last_block != 0 || c->taps.count("vit.block" + std::to_string(last)) != 0;
   bool flip = true;        // embed_preln wrote the rows in ascending order: the first LayerNorm starts from the end
+  AGB_CHECK_CUDA(cudaMemsetAsync(c->v_lncnt, 0, (size_t)(M / 256 + 2) * sizeof(int), s));
+  {                        // LayerNorm_1 of the first block; every later one is emitted by the preceding FC2
+    const EncLayerW& L0 = c->v_layers[0];
+    const bool r0 = zigzag_on() && flip;
+    flip = !flip;
+    if (int r = layernorm_f32_in(c->v_resid, 1024, M, 1024, L0.lnA_g, L0.lnA_b, 1e-5f, c->v_xln, 1024, nullptr, 0, s, r0)) return r;
+  }
   for (int l = 0; l < c->cfg.vit_layers; ++l) {
     if (l == last && !dense_last) {
       if (int r = vit_last_block_cls(c, c->v_layers[l], F, s)) return r;
       break;
     }
-    if (int r = encoder_block(c->v_layers[l], c->v_resid, c->v_xln, c->v_qkv, c->v_attn, c->v_h1, M, (int)F, 257, 257,
-                              ACT_QUICK_GELU, s, flip))
+    if (int r = encoder_block(c->v_layers[l], l + 1 < c->cfg.vit_layers ? &c->v_layers[l + 1] : nullptr, c->v_resid, c->v_xln,
+                              c->v_qkv, c->v_attn, c->v_h1, c->v_lncnt, M, (int)F, 257, 257, ACT_QUICK_GELU, s, flip))
       return r;
     tap(c, "vit.block" + std::to_string(l), c->v_resid, M * 1024 * 4, s);
   }
@@ -579,13 +596,20 @@ int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t 
   const int L = c->cfg.hubert_layers;
   bool first_pool = true;
   bool flip = true;
+  AGB_CHECK_CUDA(cudaMemsetAsync(c->h_lncnt, 0, (size_t)(M / 256 + 2) * sizeof(int), s));
+  {                        // LayerNorm of the first block; every later one is emitted by the preceding FC2
+    const EncLayerW& L0 = c->h_layers[0];
+    const bool r0 = zigzag_on() && flip;
+    flip = !flip;
+    if (int r = layernorm_f32_in(c->h_resid, 1024, M, 1024, L0.lnA_g, L0.lnA_b, 1e-5f, c->h_xln, 1024, nullptr, 0, s, r0)) return r;
+  }
   for (int l = 0; l < L; ++l) {
     if (l >= L - 3) {  // hidden_states[-4], [-3], [-2] = residual stream entering layers L-3, L-2, L-1
       if (int r = seq_mean_pool(c->h_resid, (int)G, 100, 99, nullptr, nullptr, 0.f, 0.25f, first_pool ? 0 : 1, out, s)) return r;
       first_pool = false;
     }
-    if (int r = encoder_block(c->h_layers[l], c->h_resid, c->h_xln, c->h_qkv, c->h_attn, c->h_h1, M, (int)G, 100, 99,
-                              ACT_GELU_ERF, s, flip))
+    if (int r = encoder_block(c->h_layers[l], l + 1 < L ? &c->h_layers[l + 1] : nullptr, c->h_resid, c->h_xln, c->h_qkv,
+                              c->h_attn, c->h_h1, c->h_lncnt, M, (int)G, 100, 99, ACT_GELU_ERF, s, flip))
       return r;
     tap(c, "hubert.block" + std::to_string(l), c->h_resid, M * 1024 * 4, s);
   }

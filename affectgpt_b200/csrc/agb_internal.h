@@ -79,6 +79,14 @@ struct GemmArgs {
   int nseq = 0, seq_stride = 0, seq_valid = 0;
   // walk the tiles from the last row block to the first (see encoder_block: consumers start where the producer finished)
   bool reverse = false;
+  // optional: ln_out[M, 1024] (bf16) = LayerNorm(out_f32 rows after the += ) * ln_gamma + ln_beta, fused into the kernel's
+  // tail where the shape allows (N = 1024 residual GEMM on CTA pairs), otherwise a separate pass; ln_counters: >= ceil(M/256)
+  // zero-initialised ints owned by the caller (left zero by every launch)
+  bf16* ln_out = nullptr;
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 1e-5f;
+  int* ln_counters = nullptr;
 };
 
 // tcgen05/TMEM/TMA GEMM (gemm_tcgen05.cu).  Returns 0 on success.

@@ -244,6 +244,24 @@ __device__ __forceinline__ void tma_reduce_add_3d(const void* desc, const void* 
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores committed by this thread have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk stores / reduce-adds of this thread have been PERFORMED in global memory (not merely read from smem)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// order this thread's async-proxy (TMA) global writes before its later generic-proxy operations
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int atom_add_release_gpu(int* p, int v) {
+  int old;
+  asm volatile("atom.add.release.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+// named barrier over a subset of the CTA's warps (id 1..15; nthreads a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ float tanh_approx_fwd(float x) {
   float y;
@@ -326,6 +344,46 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// LayerNorm of one 1024-wide fp32 row held by a warp: lane owns float4 v[i] = row[4 * (lane + 32 * i) .. +3], i < NV.
+// Two-pass in registers (mean, then centred sum of squares), bf16 and / or fp32 output.  ONE definition on purpose: the
+// stand-alone kernels (layernorm.cu) and the LayerNorm tail fused into the residual GEMM (gemm_tcgen05.cu) must produce
+// the same bits, so that a batch routed through either path equals its clips one at a time.
+template <int NV>
+__device__ __forceinline__ void ln_row_apply(const float4 (&v)[NV], int lane, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, float eps, __nv_bfloat16* ob_row,
+                                             float* of_row) {
+  constexpr int D = NV * 128;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (ob_row != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(y.x, y.y);
+      o.y = pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(ob_row)[lane + 32 * i] = o;
+    }
+    if (of_row != nullptr) reinterpret_cast<float4*>(of_row)[lane + 32 * i] = y;
+  }
 }
 
 }  // namespace agb

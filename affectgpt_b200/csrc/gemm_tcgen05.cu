@@ -24,6 +24,15 @@
 // positional conv (one tap per K block, TMA row coordinate shifted by tap-64, out-of-range rows
 // zero-filled by TMA = the conv's zero padding).
 //
+// LNF (fused LayerNorm tail, residual GEMMs with N = 1024 only): the LayerNorm that follows "resid += A W^T + b" in a
+// pre-LN block needs complete rows, and a tile owns only 256 of a row's 1024 columns.  The n_tiles * CG CTAs that share a
+// 256-row block therefore meet at a counter in global memory once their reduce-adds are performed; each then normalises
+// 32 of the block's rows - read back from L2, where the reduce-adds just happened, not from HBM - and writes the bf16
+// operand of the next GEMM.  The epilogue warps do this while the MMA warp is already in the next tile's main loop.  It
+// replaces a stand-alone LayerNorm pass (0.8 GB of HBM traffic per launch at C2) by a 0.27 GB write.  The arithmetic is
+// ln_row_apply (agb_ptx.cuh), the same code as the stand-alone kernel: bit-identical output.  The meeting needs all CTAs
+// of the grid co-resident: the launch is cooperative and sized by cudaOccupancyMaxActiveClusters (see launch()).
+//
 // Replaces (reference): torch.nn.Linear / Conv1d calls inside HF CLIPVisionTransformer and HubertModel
 // (transformers/models/clip/modeling_clip.py:310-350, models/hubert/modeling_hubert.py:45-231, 262-370).
 #include <cuda.h>
@@ -83,9 +92,16 @@ struct KParams {
   int reduce_f32;         // ... as an L2 reduce-add into the existing fp32 tensor (residual stream)
   int has_bf16;           // bf16 output through tmH
   int reverse;            // tile schedule walks from the last tile to the first
+  // LNF: fused LayerNorm of the rows this launch completes (resid -> bf16), see the header comment
+  const float* ln_src;    // == the fp32 output tensor (row stride 1024)
+  const float* ln_g;
+  const float* ln_b;
+  float ln_eps;
+  bf16* ln_out;           // [M, 1024]
+  int* ln_cnt;            // [m_tiles] arrival counters, zero before and after every launch
 };
 
-template <int BN, int MODE, int ACT, int CG>
+template <int BN, int MODE, int ACT, int CG, bool LNF = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmH, const KParams p) {
@@ -394,6 +410,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      if constexpr (LNF) {
+        // ---- fused LayerNorm tail.  (a) every reduce-add of this CTA's tile has been performed in L2 ...
+        if (lane == 0) {
+          tma_store_wait_all();
+          fence_proxy_async_all();
+        }
+        store_pending = false;
+        __syncwarp();
+        named_bar_sync(2, kNumEpiWarps * 32);
+        // (b) ... meet the other CTAs of this 256-row block (n_tiles * CG arrivals; the block's tiles are adjacent in
+        // the schedule, so they finish within a tile time of each other) ...
+        const int total = p.n_tiles * CG;
+        int* cnt = p.ln_cnt + mt;
+        if (ew == 0 && lane == 0) {
+          __threadfence();
+          atom_add_release_gpu(cnt, 1);
+          while (ld_acquire_gpu(cnt) < total) __nanosleep(100);
+          __threadfence();
+        }
+        named_bar_sync(2, kNumEpiWarps * 32);
+        // (c) ... and normalise this CTA's share of the block: 256 / total rows, two rows per warp in flight
+        {
+          const int rows_cta = (BM * CG) / total;                    // 32 for N = 1024
+          const int rows_warp = rows_cta / kNumEpiWarps;             // 4
+          const long long r0 = (long long)mt * (BM * CG) + (long long)(nt * CG + (int)cta_rank) * rows_cta + ew * rows_warp;
+          for (int rr = 0; rr < rows_warp; rr += 2) {
+            float4 va[8], vb[8];
+            const long long ra = r0 + rr, rb = r0 + rr + 1;
+            const bool oka = ra < p.M, okb = rb < p.M && rr + 1 < rows_warp;
+            if (oka) {
+              const float4* src = reinterpret_cast<const float4*>(p.ln_src + ra * 1024);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) va[i] = __ldcg(src + lane + 32 * i);
+            }
+            if (okb) {
+              const float4* src = reinterpret_cast<const float4*>(p.ln_src + rb * 1024);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vb[i] = __ldcg(src + lane + 32 * i);
+            }
+            if (oka) ln_row_apply<8>(va, lane, p.ln_g, p.ln_b, p.ln_eps, p.ln_out + ra * 1024, nullptr);
+            if (okb) ln_row_apply<8>(vb, lane, p.ln_g, p.ln_b, p.ln_eps, p.ln_out + rb * 1024, nullptr);
+          }
+        }
+        // (d) second arrival: whoever completes the count puts the counter back to zero for the next launch
+        __syncwarp();
+        named_bar_sync(2, kNumEpiWarps * 32);
+        if (ew == 0 && lane == 0) {
+          if (atom_add_release_gpu(cnt, 1) == 2 * total - 1) *reinterpret_cast<volatile int*>(cnt) = 0;
+        }
+      }
     }
     if (store_pending && lane == 0) tma_store_wait_read();   // staging must outlive the last bulk store's read
   }
@@ -457,33 +523,61 @@ struct Maps {
   CUtensorMap a, b, f, h;
 };
 
-template <int BN, int MODE, int ACT, int CG>
+template <int BN, int MODE, int ACT, int CG, bool LNF = false>
 int launch(const Maps& m, const KParams& kp, cudaStream_t stream) {
-  auto kern = gemm_kernel<BN, MODE, ACT, CG>;
+  auto kern = gemm_kernel<BN, MODE, ACT, CG, LNF>;
   using C = Cfg<BN, CG, MODE == A_POSCONV_SLAB>;
   static bool configured = false;
+  static int max_units = 0;                               // LNF: clusters that are guaranteed to be co-resident
   if (!configured) {
     AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int tiles = kp.m_tiles * kp.n_tiles;
-  const int units = num_sms() / CG;                       // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
-  const int grid = (tiles < units ? tiles : units) * CG;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  int units = num_sms() / CG;                             // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+  if constexpr (LNF) {
+    // the CTAs of a row block wait for each other inside the kernel: every CTA of the grid must be resident at once.
+    // Size the grid by what the hardware can co-schedule (pairs need two free SMs of one GPC) and make the launch
+    // cooperative, so that an impossible placement is a launch error instead of a hang.
+    static_assert(CG == 2, "LNF runs on CTA pairs");
+    if (max_units == 0) {
+      cfg.gridDim = dim3((unsigned)(units * CG));
+      int n = 0;
+      AGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      AGB_REQUIRE(n > 0, "gemm: no co-resident cluster placement for the fused-LayerNorm kernel");
+      max_units = n;
+    }
+    if (units > max_units) units = max_units;
+    static int coop = -1;                 // AGB_LNF_COOP=1: also mark the launch cooperative (diagnostics)
+    if (coop < 0) { const char* e = getenv("AGB_LNF_COOP"); coop = (e && e[0] == '1') ? 1 : 0; }
+    if (coop) {
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.numAttrs = 2;
+    }
+  }
+  const int grid = (tiles < units ? tiles : units) * CG;
+  cfg.gridDim = dim3((unsigned)grid);
   AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.f, m.h, kp));
   AGB_CHECK_LAUNCH();
   return 0;
+}
+
+// AGB_FUSED_LN=0: LayerNorm always as its own pass after the residual GEMM (A/B runs, bit-identical results)
+bool fused_ln_on() {                     // read per call: tools/ab_graph.py captures one graph per setting in one process
+  const char* e = getenv("AGB_FUSED_LN");
+  return !(e != nullptr && e[0] == '0');
 }
 
 bool use_pairs() {
@@ -546,6 +640,21 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   // CTA pairs pay off once there are enough 256-row tiles to fill the machine
   const bool pairs = use_pairs() && a.mode != A_POSCONV && a.M >= 2048;
   const int cg = pairs ? 2 : 1;
+  // fused LayerNorm tail (see the header comment): residual GEMMs with complete 1024-wide rows on CTA pairs; any other
+  // shape runs the plain kernel followed by the stand-alone LayerNorm (same arithmetic, same bits)
+  const bool want_ln = a.ln_out != nullptr;
+  if (want_ln)
+    AGB_REQUIRE(a.ln_gamma && a.ln_beta && a.res != nullptr && a.out_f32 != nullptr && a.N == 1024,
+                "gemm: the fused LayerNorm needs gamma / beta and a 1024-wide fp32 residual output");
+  const bool fuse_ln = want_ln && fused_ln_on() && pairs && a.mode == A_PLAIN && a.act == ACT_NONE && a.ld_f32 == 1024 &&
+                       a.ln_counters != nullptr;
+  kp.ln_src = a.out_f32; kp.ln_g = a.ln_gamma; kp.ln_b = a.ln_beta; kp.ln_eps = a.ln_eps; kp.ln_out = a.ln_out;
+  kp.ln_cnt = a.ln_counters;
+  auto ln_after = [&]() -> int {            // fallback: separate pass, walking the rows in the opposite direction
+    if (!want_ln || fuse_ln) return 0;
+    return layernorm_f32_in(a.out_f32, a.ld_f32, a.M, 1024, a.ln_gamma, a.ln_beta, a.ln_eps, a.ln_out, 1024, nullptr, 0, stream,
+                            !a.reverse);
+  };
 
   Maps m{};
   const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, F32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -607,6 +716,12 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     if (a.act == ACT_NONE) return pairs ? launch<256, A_CONV3, ACT_NONE, 2>(m, kp, stream) : launch<256, A_CONV3, ACT_NONE, 1>(m, kp, stream);
     if (a.act == ACT_GELU_ERF) return pairs ? launch<256, A_CONV3, ACT_GELU_ERF, 2>(m, kp, stream) : launch<256, A_CONV3, ACT_GELU_ERF, 1>(m, kp, stream);
     AGB_REQUIRE(false, "gemm: unsupported activation for conv3 mode");
+  }
+  if (fuse_ln) return launch<256, A_PLAIN, ACT_NONE, 2, true>(m, kp, stream);
+  if (want_ln) {
+    AGB_REQUIRE(a.act == ACT_NONE, "gemm: LayerNorm output is only offered for the residual GEMMs (no activation)");
+    if (int r = pairs ? launch<256, A_PLAIN, ACT_NONE, 2>(m, kp, stream) : launch<256, A_PLAIN, ACT_NONE, 1>(m, kp, stream)) return r;
+    return ln_after();
   }
   switch (a.act) {
     case ACT_NONE: return pairs ? launch<256, A_PLAIN, ACT_NONE, 2>(m, kp, stream) : launch<256, A_PLAIN, ACT_NONE, 1>(m, kp, stream);

@@ -15,45 +15,15 @@ __global__ void __launch_bounds__(256) ln_f32_kernel(const float* __restrict__ x
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                     float eps, bf16* __restrict__ ob, long long ldb,
                                                     float* __restrict__ of, long long ldf, int reverse) {
-  constexpr int D = NV * 128;
   const long long r0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r0 >= rows) return;
   const long long row = reverse ? rows - 1 - r0 : r0;       // last rows first: they are what the producer left in L2
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   float4 v[NV];
-  float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = xr[lane + 32 * i];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(s) * (1.0f / D);
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    ss += (a * a + b * b) + (c * c + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
-    float4 y;
-    y.x = (v[i].x - mean) * rstd * g.x + b.x;
-    y.y = (v[i].y - mean) * rstd * g.y + b.y;
-    y.z = (v[i].z - mean) * rstd * g.z + b.z;
-    y.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (ob != nullptr) {
-      uint2 o;
-      o.x = pack_bf16x2(y.x, y.y);
-      o.y = pack_bf16x2(y.z, y.w);
-      reinterpret_cast<uint2*>(ob + row * ldb)[lane + 32 * i] = o;
-    }
-    if (of != nullptr) reinterpret_cast<float4*>(of + row * ldf)[lane + 32 * i] = y;
-  }
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  ln_row_apply<NV>(v, lane, gamma, beta, eps, ob != nullptr ? ob + row * ldb : nullptr, of != nullptr ? of + row * ldf : nullptr);
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {

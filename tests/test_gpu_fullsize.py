@@ -105,7 +105,7 @@ def test_graphed_step_is_bit_identical_and_reusable(full_path):
     from affectgpt_b200 import synthetic as S
     B = 4
     g = agb.GraphedClipBatch(full_path, B, 8, 8, device=DEV)
-    assert g.kernels_per_replay > 300
+    assert g.kernels_per_replay > 250                               # 5 kernels per encoder block + front-ends + heads
     for seed in (61, 62):                                           # two different batches through the same graph
         frames, audio = S.frames(B, 8, seed=seed).to(DEV), S.audio(B, 8, seed=seed + 10).to(DEV)
         out = g(frames, audio)
