@@ -301,6 +301,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int sw = lane & 7;                             // 128B swizzle: 16-byte chunk index ^= row % 8
     bool store_pending = false;
     int it = 0;
+    // LNF: the row block (mt, nt) whose LayerNorm share this CTA still owes (see the header comment)
+    int pend_mt = -1, pend_nt = 0;
+    auto ln_share = [&](int bmt, int bnt) {
+      // (a) meet the other CTAs of the 256-row block: n_tiles * CG first arrivals = all of its reduce-adds are in L2
+      const int total = p.n_tiles * CG;
+      int* cnt = p.ln_cnt + bmt;
+      if (ew == 0 && lane == 0) {
+        while (ld_acquire_gpu(cnt) < total) __nanosleep(64);
+        __threadfence();
+      }
+      named_bar_sync(2, kNumEpiWarps * 32);
+      // (b) normalise this CTA's share of the block: 256 / total rows, two rows per warp in flight, read from L2
+      const int rows_cta = (BM * CG) / total;                    // 32 for N = 1024
+      const int rows_warp = rows_cta / kNumEpiWarps;             // 4
+      const long long r0 = (long long)bmt * (BM * CG) + (long long)(bnt * CG + (int)cta_rank) * rows_cta + ew * rows_warp;
+      for (int rr = 0; rr < rows_warp; rr += 2) {
+        float4 va[8], vb[8];
+        const long long ra = r0 + rr, rb = r0 + rr + 1;
+        const bool oka = ra < p.M, okb = rb < p.M && rr + 1 < rows_warp;
+        if (oka) {
+          const float4* src = reinterpret_cast<const float4*>(p.ln_src + ra * 1024);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) va[i] = __ldcg(src + lane + 32 * i);
+        }
+        if (okb) {
+          const float4* src = reinterpret_cast<const float4*>(p.ln_src + rb * 1024);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vb[i] = __ldcg(src + lane + 32 * i);
+        }
+        if (oka) ln_row_apply<8>(va, lane, p.ln_g, p.ln_b, p.ln_eps, p.ln_out + ra * 1024, nullptr);
+        if (okb) ln_row_apply<8>(vb, lane, p.ln_g, p.ln_b, p.ln_eps, p.ln_out + rb * 1024, nullptr);
+      }
+      // (c) second arrival: whoever completes the count puts the counter back to zero for the next launch
+      __syncwarp();
+      named_bar_sync(2, kNumEpiWarps * 32);
+      if (ew == 0 && lane == 0) {
+        if (atom_add_release_gpu(cnt, 1) == 2 * total - 1) *reinterpret_cast<volatile int*>(cnt) = 0;
+      }
+    };
     for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int tl = p.reverse ? num_tiles - 1 - tile : tile;
       const int mt = tl / p.n_tiles, nt = tl % p.n_tiles;
@@ -411,7 +450,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if constexpr (LNF) {
-        // ---- fused LayerNorm tail.  (a) every reduce-add of this CTA's tile has been performed in L2 ...
+        // ---- fused LayerNorm tail, one tile behind: first this CTA's share of the PREVIOUS tile's row block (whose
+        // other CTAs arrived a tile ago, so the meeting costs no waiting; meanwhile this tile's reduce-adds complete) ...
+        if (pend_mt >= 0) ln_share(pend_mt, pend_nt);
+        // ... then the arrival for this tile: every reduce-add of this CTA's tile has been performed in L2
         if (lane == 0) {
           tma_store_wait_all();
           fence_proxy_async_all();
@@ -419,47 +461,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         store_pending = false;
         __syncwarp();
         named_bar_sync(2, kNumEpiWarps * 32);
-        // (b) ... meet the other CTAs of this 256-row block (n_tiles * CG arrivals; the block's tiles are adjacent in
-        // the schedule, so they finish within a tile time of each other) ...
-        const int total = p.n_tiles * CG;
-        int* cnt = p.ln_cnt + mt;
         if (ew == 0 && lane == 0) {
           __threadfence();
-          atom_add_release_gpu(cnt, 1);
-          while (ld_acquire_gpu(cnt) < total) __nanosleep(100);
-          __threadfence();
+          atom_add_release_gpu(p.ln_cnt + mt, 1);
         }
-        named_bar_sync(2, kNumEpiWarps * 32);
-        // (c) ... and normalise this CTA's share of the block: 256 / total rows, two rows per warp in flight
-        {
-          const int rows_cta = (BM * CG) / total;                    // 32 for N = 1024
-          const int rows_warp = rows_cta / kNumEpiWarps;             // 4
-          const long long r0 = (long long)mt * (BM * CG) + (long long)(nt * CG + (int)cta_rank) * rows_cta + ew * rows_warp;
-          for (int rr = 0; rr < rows_warp; rr += 2) {
-            float4 va[8], vb[8];
-            const long long ra = r0 + rr, rb = r0 + rr + 1;
-            const bool oka = ra < p.M, okb = rb < p.M && rr + 1 < rows_warp;
-            if (oka) {
-              const float4* src = reinterpret_cast<const float4*>(p.ln_src + ra * 1024);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) va[i] = __ldcg(src + lane + 32 * i);
-            }
-            if (okb) {
-              const float4* src = reinterpret_cast<const float4*>(p.ln_src + rb * 1024);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vb[i] = __ldcg(src + lane + 32 * i);
-            }
-            if (oka) ln_row_apply<8>(va, lane, p.ln_g, p.ln_b, p.ln_eps, p.ln_out + ra * 1024, nullptr);
-            if (okb) ln_row_apply<8>(vb, lane, p.ln_g, p.ln_b, p.ln_eps, p.ln_out + rb * 1024, nullptr);
-          }
-        }
-        // (d) second arrival: whoever completes the count puts the counter back to zero for the next launch
-        __syncwarp();
-        named_bar_sync(2, kNumEpiWarps * 32);
-        if (ew == 0 && lane == 0) {
-          if (atom_add_release_gpu(cnt, 1) == 2 * total - 1) *reinterpret_cast<volatile int*>(cnt) = 0;
-        }
+        pend_mt = mt;
+        pend_nt = nt;
       }
+    }
+    if constexpr (LNF) {
+      if (pend_mt >= 0) ln_share(pend_mt, pend_nt);
     }
     if (store_pending && lane == 0) tma_store_wait_read();   // staging must outlive the last bulk store's read
   }
@@ -574,10 +585,16 @@ int launch(const Maps& m, const KParams& kp, cudaStream_t stream) {
   return 0;
 }
 
-// AGB_FUSED_LN=0: LayerNorm always as its own pass after the residual GEMM (A/B runs, bit-identical results)
-bool fused_ln_on() {                     // read per call: tools/ab_graph.py captures one graph per setting in one process
+// AGB_FUSED_LN=1: LayerNorm in the residual GEMM's tail instead of its own pass (bit-identical results)
+// Off by default.  Measured on B200 in one process, graphs replayed alternately (tools/ab_graph.py, 30 rounds, C2 step):
+// fused 123.7 ms vs separate LayerNorm passes 120.6 ms, although the LayerNorm category drops from 10.2 to 1.9 ms and 51 GB
+// of HBM reads per step disappear.  The step runs against the 1 kW power cap, where time follows joules: the stand-alone
+// pass costs 0.118 J (profiles/r02_energy_probe.jsonl), of which only the DRAM read (~0.02 J) is saved, and the tail costs
+// the GEMM more than that (168 registers with spills, epilogue warps busy while the tensor pipe waits).  Kept opt-in and
+// tested for bit-identity (tests/test_gpu_kernels.py); read per call so one process can capture a graph per setting.
+bool fused_ln_on() {
   const char* e = getenv("AGB_FUSED_LN");
-  return !(e != nullptr && e[0] == '0');
+  return e != nullptr && e[0] == '1';
 }
 
 bool use_pairs() {

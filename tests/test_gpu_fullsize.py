@@ -201,3 +201,25 @@ def test_outlier_channels_in_the_residual_stream(scale):
     gate(at["hubert.block4"].reshape(2, 100, 1024)[:, :99], ahs[5], f"outlier x{scale:g}: hubert.block4")
     gate(got_a, want_a, f"outlier x{scale:g}: hubert features")
     eng.close()
+
+
+def test_fused_layernorm_tail_is_bit_identical(full_path, monkeypatch):
+    """AGB_FUSED_LN=1 moves every LayerNorm that follows a residual GEMM into that GEMM's tail (the CTAs of a 256-row block
+    meet at a counter and normalise the rows from L2; gemm_tcgen05.cu 'LNF').  Same arithmetic (ln_row_apply), so the tokens
+    must not change by a bit - including odd row counts (partial last block) and repeated launches (counters back at zero)."""
+    from affectgpt_b200 import engine as E, synthetic as S
+    for B in (4, 9):                                                # 9 clips: 72 frames = 18504 rows, 72.3 row blocks
+        frames, audio = S.frames(B, 8, seed=81 + B).to(DEV), S.audio(B, 8, seed=91 + B).to(DEV)
+        want, _ = _tokens(full_path, frames, audio)
+        n0 = E.launch_count()
+        want2, _ = _tokens(full_path, frames, audio)
+        plain_launches = E.launch_count() - n0
+        monkeypatch.setenv("AGB_FUSED_LN", "1")
+        for rep in range(3):
+            n0 = E.launch_count()
+            got, _ = _tokens(full_path, frames, audio)
+            fused_launches = E.launch_count() - n0
+            assert torch.equal(got, want), (B, rep)
+        monkeypatch.delenv("AGB_FUSED_LN")
+        assert torch.equal(want2, want)
+        assert fused_launches < plain_launches - 80, (fused_launches, plain_launches)    # 2 x (23 + 24) passes are gone
