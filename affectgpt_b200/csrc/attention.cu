@@ -5,8 +5,9 @@
 // whole CTA, each warp takes 16-query slices, holds the full score row block (16 x S_pad, fp32) in
 // registers, does an exact fp32 softmax (no online rescaling needed at these lengths), converts P to
 // bf16 in place (accumulator layout == A-operand layout) and multiplies by V.
-// Tensor-core path in this round: mma.sync.m16n8k16 bf16 (HMMA) -- attention is 4% of ViT FLOPs;
-// the tcgen05 version is planned work.
+// mma.sync.m16n8k16 bf16 (HMMA).  NOT on the path's shapes: ViT (257 tokens) and HuBERT (99) run the tcgen05 kernel in
+// attention_tc2.cu; this kernel is the general fallback for the lengths that one has no instantiation for (113..128 and
+// 258..272 tokens), exercised by tests/test_gpu_kernels.py::test_attention_vs_sdpa.
 //
 // Replaces: CLIPAttention.forward (modeling_clip.py:262-332, scale 1/8, fp32 softmax) and
 // HubertAttention.forward (modeling_hubert.py:262-370).
@@ -194,12 +195,9 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
               "attention: alignment");
   LaunchTimer timer(PROF_ATTENTION, 4.0 * nseq * 16.0 * (double)seq_valid * seq_valid * 64.0,
                     (double)nseq * seq_valid * 4096.0 * 2.0, s);
-  static int force_hmma = -1;   // AGB_ATTENTION=hmma forces the mma.sync kernel (A/B comparisons, tools/attn_bench.py)
-  if (force_hmma < 0) {
-    const char* e = getenv("AGB_ATTENTION");
-    force_hmma = (e != nullptr && e[0] == 'h') ? 1 : 0;
-  }
-  if (!force_hmma) {
+  // tcgen05 kernel for the shapes of the path (<= 112 and 129..257 tokens: HuBERT 99, ViT 257); the register-resident
+  // mma.sync kernel below covers the remaining lengths up to 272 (113..128, 258..272) so that the op stays general
+  {
     const int r = attention_tc2(qkv, out, nseq, seq_stride, seq_valid, scale, s, reverse);
     if (r >= 0) return r;
   }

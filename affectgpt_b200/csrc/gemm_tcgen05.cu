@@ -31,7 +31,8 @@
 // operand of the next GEMM.  The epilogue warps do this while the MMA warp is already in the next tile's main loop.  It
 // replaces a stand-alone LayerNorm pass (0.8 GB of HBM traffic per launch at C2) by a 0.27 GB write.  The arithmetic is
 // ln_row_apply (agb_ptx.cuh), the same code as the stand-alone kernel: bit-identical output.  The meeting needs all CTAs
-// of the grid co-resident: the launch is cooperative and sized by cudaOccupancyMaxActiveClusters (see launch()).
+// of the grid co-resident: the grid is sized by cudaOccupancyMaxActiveClusters (see launch()); two such kernels must not
+// share the GPU (AGB_OVERLAP=1 and this switch exclude each other).  Opt-in (AGB_FUSED_LN=1): see fused_ln_on().
 //
 // Replaces (reference): torch.nn.Linear / Conv1d calls inside HF CLIPVisionTransformer and HubertModel
 // (transformers/models/clip/modeling_clip.py:310-350, models/hubert/modeling_hubert.py:45-231, 262-370).
@@ -60,26 +61,19 @@ constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
 constexpr int kStageBufBytes = 4096;  // per epilogue warp: 32 rows x 128 B, 128B-swizzled (TMA store source)
 
-constexpr int A_POSCONV_SLAB = 3;     // internal variant of A_POSCONV: the A operand is a resident input slab (see below)
-constexpr int kSlabRows = 256;        // 128 output rows + 127 taps of halo (+1), 128 B each
-
-template <int BN, int CG, bool SLAB = false>
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int kABytes = SLAB ? 0 : BM * BK * 2;        // slab mode: the ring carries W only
+  static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / CG) * BK * 2;            // per CTA: the pair splits W's rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSlabBytes = SLAB ? kSlabRows * 128 : 0; // two slabs (this tile's and the next one's)
   static constexpr int kEpiBytes = kNumEpiWarps * kStageBufBytes;
   static constexpr int kBarBytes = 512;                         // 2 * kStages + 8 mbarriers + the TMEM slot
-  static constexpr int kBudget = 232448 - 1024 - kBarBytes - kEpiBytes - 2 * kSlabBytes;
-  static constexpr int kMaxStages = SLAB ? 14 : 8;              // slab mode: 8 KB stages, deep ring hides the L2 latency
+  static constexpr int kBudget = 232448 - 1024 - kBarBytes - kEpiBytes;
+  static constexpr int kMaxStages = 8;
   static constexpr int kStages = kBudget / kStageBytes > kMaxStages ? kMaxStages : kBudget / kStageBytes;
-  // slab mode: consecutive taps accumulate into kAcc independent TMEM tiles (summed by the epilogue) - with N = 64 a
-  // tcgen05.mma is 32 clk of tensor work, far less than the latency of a dependent accumulate into the same tile
-  static constexpr int kAcc = SLAB ? 4 : 1;
-  static constexpr int kTmemCols = 2 * BN * kAcc;               // two accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kSlabBytes + kEpiBytes + 1024 /*align*/ + kBarBytes;
-  static_assert((kStages * kStageBytes) % 1024 == 0, "slabs / staging buffers need 1024-byte alignment");
+  static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + kBarBytes;
+  static_assert((kStages * kStageBytes) % 1024 == 0, "staging buffers need 1024-byte alignment");
   static_assert((2 * kStages + 8) * 8 + 16 <= kBarBytes, "barrier region");
 };
 
@@ -105,9 +99,8 @@ template <int BN, int MODE, int ACT, int CG, bool LNF = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmH, const KParams p) {
-  constexpr bool kSlab = MODE == A_POSCONV_SLAB;
-  constexpr bool kPos = MODE == A_POSCONV || kSlab;
-  using C = Cfg<BN, CG, kSlab>;
+  constexpr bool kPos = MODE == A_POSCONV;
+  using C = Cfg<BN, CG>;
   constexpr int S = C::kStages;
   static_assert(CG == 1 || !kPos, "the positional-conv modes run single-CTA");
   extern __shared__ uint8_t smem_raw[];
@@ -115,16 +108,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + S * C::kABytes;
-  uint8_t* smS = smem + S * C::kStageBytes;                       // slab mode: two input slabs, 1024-aligned
-  uint8_t* smE = smS + 2 * C::kSlabBytes;                         // epilogue staging, 1024-aligned
+  uint8_t* smE = smem + S * C::kStageBytes;                       // epilogue staging, 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(smE + C::kEpiBytes);
   uint64_t* full = bars;            // [S]  TMA -> MMA
   uint64_t* empty = bars + S;       // [S]  MMA -> TMA
   uint64_t* tfull = bars + 2 * S;   // [2]  MMA -> epilogue
   uint64_t* tempty = tfull + 2;     // [2]  epilogue -> MMA
-  uint64_t* sfull = tempty + 2;     // [2]  slab mode: TMA -> MMA (input slab resident)
-  uint64_t* sempty = sfull + 2;     // [2]  slab mode: MMA -> TMA (all taps of the tile have read it)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -145,8 +135,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kNumEpiWarps * CG);
-      mbar_init(&sfull[i], 1);
-      mbar_init(&sempty[i], 1);
     }
     fence_mbar_init();
   }
@@ -170,23 +158,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      int sit = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++sit) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int tl = p.reverse ? num_tiles - 1 - tile : tile;
         const int mt = tl / p.n_tiles, nt = tl % p.n_tiles;
         const int row0 = mt * (BM * CG) + (int)cta_rank * BM;          // this CTA's 128 A rows
         const int wrow0 = nt * BN + (int)cta_rank * (BN / CG);          // this CTA's share of the W tile
-        if constexpr (kSlab) {
-          // rows t - 64 .. t + 191 of sequence mt, the 64 input channels of group nt: every tap's A tile is a
-          // 128-row window of this slab (TMA zero-fills rows outside [0, valid) = the conv's zero padding)
-          const int si = sit & 1;
-          mbar_wait(&sempty[si], ((sit >> 1) & 1) ^ 1u, 6);
-          if (issuer) {
-            mbar_arrive_expect_tx(&sfull[si], C::kSlabBytes);
-            tma_load_3d(smS + si * C::kSlabBytes, &tmA, &sfull[si], nt * 64, -64, mt, kEvictNormal);
-          }
-          __syncwarp();
-        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 1);
           void* dA = smA + stage * C::kABytes;
@@ -235,46 +211,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty[as], aphase ^ 1u, 2);
         tc_fence_after();
-        const uint32_t tmem_d0 = tmem_base + as * (BN * C::kAcc);
-        uint32_t slab_addr = 0;
-        if constexpr (kSlab) {
-          mbar_wait(&sfull[it & 1], (it >> 1) & 1, 7);
-          slab_addr = smem_u32(smS + (it & 1) * C::kSlabBytes);
-        }
+        const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 3);
           tc_fence_after();
-          uint64_t da;
-          if constexpr (kSlab) {
-            // tap kb: output row m reads slab row m + kb -> the A tile starts kb rows (kb * 128 B) into the slab.  The
-            // 128B swizzle is a function of the absolute shared-memory address (the slab is 1024-byte aligned), so a
-            // start address that is not 8-row aligned needs nothing else: measured on B200, the descriptor's
-            // matrix-base-offset field must stay 0 here (setting it to (start >> 7) & 7 gives wrong products).
-            da = umma_desc_kmajor_sw128(slab_addr + (uint32_t)kb * 128u);
-          } else {
-            da = umma_desc_kmajor_sw128(smem_u32(smA + stage * C::kABytes));
-          }
-          const uint32_t tmem_d = tmem_d0 + (kSlab ? (uint32_t)(kb & (C::kAcc - 1)) * BN : 0u);
-          const int kb_acc = kSlab ? kb / C::kAcc : kb;          // first K block of THIS accumulator overwrites
+          const uint64_t da = umma_desc_kmajor_sw128(smem_u32(smA + stage * C::kABytes));
           const uint64_t db = umma_desc_kmajor_sw128(smem_u32(smB + stage * C::kBBytes));
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
               if constexpr (CG == 2)
-                umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb_acc | k) != 0 ? 1u : 0u);
+                umma_bf16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
               else
-                umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb_acc | k) != 0 ? 1u : 0u);
+                umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if constexpr (CG == 2) {
               umma_commit_pair(&empty[stage], 0x3);                        // smem slot free in both CTAs
               if (kb == p.num_kb - 1) umma_commit_pair(&tfull[as], 0x3);   // accumulator complete in both CTAs
             } else {
               umma_commit(&empty[stage]);
-              if (kb == p.num_kb - 1) {
-                umma_commit(&tfull[as]);
-                if constexpr (kSlab) umma_commit(&sempty[it & 1]);
-              }
+              if (kb == p.num_kb - 1) umma_commit(&tfull[as]);
             }
           }
           __syncwarp();
@@ -350,22 +307,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       mbar_wait(&tfull[as], aphase, 4);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * (BN * C::kAcc) + half * HC);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + half * HC);
 
       uint32_t v[2][32];
       tmem_ld_32x32b_x32(taddr, v[0]);
-      if constexpr (kSlab) {
-        // fold the other accumulators of the tap round-robin into the first one (NCH == 1 here)
-        static_assert(!kSlab || NCH == 1, "slab mode: one 32-column chunk per warp");
-#pragma unroll
-        for (int a2 = 1; a2 < C::kAcc; ++a2) {
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + a2 * BN, v[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[0][j] = __float_as_uint(__uint_as_float(v[0][j]) + __uint_as_float(v[1][j]));
-        }
-      }
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
@@ -537,7 +482,7 @@ struct Maps {
 template <int BN, int MODE, int ACT, int CG, bool LNF = false>
 int launch(const Maps& m, const KParams& kp, cudaStream_t stream) {
   auto kern = gemm_kernel<BN, MODE, ACT, CG, LNF>;
-  using C = Cfg<BN, CG, MODE == A_POSCONV_SLAB>;
+  using C = Cfg<BN, CG>;
   static bool configured = false;
   static int max_units = 0;                               // LNF: clusters that are guaranteed to be co-resident
   if (!configured) {
@@ -597,29 +542,6 @@ bool fused_ln_on() {
   return e != nullptr && e[0] == '1';
 }
 
-bool use_pairs() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AGB_GEMM_CTA_GROUP");     // bring-up switch: 1 = single-CTA tiles everywhere
-    v = (e != nullptr && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-// Positional conv A operand.  Default "tap": one TMA A tile per tap (3 MB of operands per 128 x 64 tile, all L2 hits).
-// AGB_POSCONV=slab: resident input slab, every tap's A tile is a row-shifted window of it (1 MB of W per tile) with four
-// round-robin accumulators.  Measured on B200 once the issue waterfall was gone: tap 1.88 ms, slab 2.02 ms per 512
-// sequences (the unaligned windows read shared memory less efficiently than the L2 serves whole tiles), so the slab
-// variant stays an experiment - it is the starting point for sharing W between sequences.
-int posconv_slab_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AGB_POSCONV");
-    v = (e && !strcmp(e, "slab")) ? 1 : 0;
-  }
-  return v;
-}
-
 }  // namespace
 
 int make_tmap_generic(CUtensorMap* out, int dtype_is_f32, const void* base, int rank, const uint64_t* dims,
@@ -655,7 +577,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   AGB_REQUIRE(!(a.out_f32 && a.out_bf16), "gemm: exactly one output (fp32 or bf16)");
 
   // CTA pairs pay off once there are enough 256-row tiles to fill the machine
-  const bool pairs = use_pairs() && a.mode != A_POSCONV && a.M >= 2048;
+  const bool pairs = a.mode != A_POSCONV && a.M >= 2048;
   const int cg = pairs ? 2 : 1;
   // fused LayerNorm tail (see the header comment): residual GEMMs with complete 1024-wide rows on CTA pairs; any other
   // shape runs the plain kernel followed by the stand-alone LayerNorm (same arithmetic, same bits)
@@ -697,7 +619,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
                 "gemm: posconv writes resid += gelu(conv) (fp32, row stride 1024)");
     uint64_t dA[3] = {1024, (uint64_t)a.seq_valid, (uint64_t)a.nseq};
     uint64_t sA[2] = {1024 * 2, (uint64_t)a.seq_stride * 1024 * 2};
-    if (int r = make_tmap(&m.a, BF, a.A, 3, dA, sA, 64, posconv_slab_mode() ? kSlabRows : BM)) return r;
+    if (int r = make_tmap(&m.a, BF, a.A, 3, dA, sA, 64, BM)) return r;
     uint64_t sF[2] = {1024 * 4, (uint64_t)a.seq_stride * 1024 * 4};
     if (int r = make_tmap(&m.f, F32, a.out_f32, 3, dA, sF, 32, 32)) return r;   // rows >= seq_valid are clipped
     kp.num_kb = 128;
@@ -722,9 +644,6 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     if (int r = make_tmap(&m.b, BF, a.W, 2, dB, sB, 64, 64)) return r;
     kp.n_tiles = 16;
     AGB_REQUIRE(a.act == ACT_GELU_ERF, "gemm: posconv epilogue is bias + GELU (+ residual)");
-    if (posconv_slab_mode()) {
-      return launch<64, A_POSCONV_SLAB, ACT_GELU_ERF, 1>(m, kp, stream);
-    }
     return launch<64, A_POSCONV, ACT_GELU_ERF, 1>(m, kp, stream);
   }
   if (int r = make_tmap(&m.b, BF, a.W, 2, dB, sB, 64, 256 / cg)) return r;

@@ -314,15 +314,10 @@ int hubert_conv0(const float* wav, const float* stats, int64_t seg_per_group, in
   LaunchTimer timer(PROF_FRONTEND, 2.0 * nseg * 6399.0 * 512 * 10, (double)nseg * (32000.0 * 4 + 6400.0 * 512 * 2), s);
   dim3 grid((kL0Pad + kRowsPerBlock - 1) / kRowsPerBlock, (unsigned)nseg);
   if (norm_mode == 0) {
-    static int simt = -1;        // AGB_CONV0=simt keeps the CUDA-core kernel (A/B comparisons)
-    if (simt < 0) {
-      const char* e = getenv("AGB_CONV0");
-      simt = (e != nullptr && e[0] == 's') ? 1 : 0;
-    }
-    if (!simt && gn_scratch != nullptr)   // tensor-core path: gn_scratch doubles as the 32 KB packed-filter buffer
-      return hubert_conv0_layer_tc(wav, stats, seg_per_group, seg_offset, nseg, w, bias, g, b,
-                                   reinterpret_cast<bf16*>(gn_scratch), out, s);
-    conv0_kernel<0><<<grid, 256, 0, s>>>(wav, stats, seg_per_group, seg_offset, w, bias, g, b, nullptr, out);
+    // "layer" variant: tensor-core kernel (conv0_tc.cu); gn_scratch doubles as its 32 KB packed-filter buffer
+    AGB_REQUIRE(gn_scratch != nullptr, "conv0: scratch missing");
+    return hubert_conv0_layer_tc(wav, stats, seg_per_group, seg_offset, nseg, w, bias, g, b,
+                                 reinterpret_cast<bf16*>(gn_scratch), out, s);
   } else {
     AGB_REQUIRE(gn_scratch != nullptr, "conv0: group-norm scratch missing");
     double* acc = reinterpret_cast<double*>(gn_scratch);

@@ -52,19 +52,46 @@ class _EncoderBase(nn.Module):
         self._engine_cfg: dict = {}
         self._device_hint: Optional[torch.device] = None
 
-    # nn.Module plumbing the reference's callers use: .to(device), .eval(), named_parameters() (frozen / none)
+    # nn.Module plumbing the reference's callers use: .to(device), .eval(), named_parameters() (frozen / none).
+    # A dtype request cannot be honoured - the kernels compute with bf16 operands / fp32 accumulation and return fp32 at
+    # this boundary - so anything but float32 raises instead of being silently ignored.
+    _PRECISION_MSG = ("{cls} computes with bf16 operands and fp32 accumulation inside libagb and returns float32; "
+                      "it cannot be cast to {dtype} (cast the returned features instead)")
+
+    def _reject_dtype(self, dtype) -> None:
+        if dtype is not None and dtype != torch.float32:
+            raise TypeError(self._PRECISION_MSG.format(cls=type(self).__name__, dtype=dtype))
+
     def to(self, *args, **kwargs):
-        for a in list(args) + list(kwargs.values()):
-            if isinstance(a, (str, torch.device)):
-                try:
-                    self._device_hint = torch.device(a)
-                except (RuntimeError, TypeError):
-                    pass
+        device = kwargs.get("device")
+        dtype = kwargs.get("dtype")
+        for a in args:
+            if isinstance(a, torch.dtype):
+                dtype = a
+            elif isinstance(a, (str, torch.device, int)):
+                device = a
+            elif isinstance(a, torch.Tensor):                   # .to(other): that tensor's device and dtype
+                device, dtype = a.device, a.dtype
+        self._reject_dtype(dtype)
+        if device is not None:
+            self._device_hint = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         return self
 
     def cuda(self, device=None):
         self._device_hint = torch.device("cuda", device if isinstance(device, int) else 0)
         return self
+
+    def float(self):
+        return self
+
+    def half(self):
+        self._reject_dtype(torch.float16)
+
+    def bfloat16(self):
+        self._reject_dtype(torch.bfloat16)
+
+    def double(self):
+        self._reject_dtype(torch.float64)
 
     def load_hf_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
         """Provide the HuggingFace checkpoint tensors (keys of SURVEY appendix B); uploaded on first use."""

@@ -71,6 +71,10 @@ class AffectGPTFusion(nn.Module):
                     raise ValueError(f"engine was created with qf_{which}_queries={engine.qf_queries[which]}, need {nq}")
         self._fusion_state: Optional[Dict[str, torch.Tensor]] = None
         self.overlap_encoders = os.environ.get("AGB_OVERLAP", "0") == "1"   # audio chain on a side stream (opt-in)
+        if self.overlap_encoders and os.environ.get("AGB_FUSED_LN") == "1":
+            # the fused-LayerNorm GEMM makes its CTAs wait for each other and therefore needs the whole GPU: two such
+            # kernels on two streams could starve each other of SMs (gemm_tcgen05.cu, "LNF")
+            self.overlap_encoders = False
         self._side_streams: Dict[torch.device, torch.cuda.Stream] = {}
         if engine is not None:
             for enc in (visual_encoder, acoustic_encoder):

@@ -93,3 +93,22 @@ def test_resample_filter_bank_is_torchaudios():
         assert bank.shape == (n, 2 * width + o) and torch.equal(bank, ref[:, 0, :])
     with pytest.raises(ValueError):
         staging.resample_bank(44100.5, 16000)
+
+
+def test_encoder_to_accepts_devices_and_rejects_dtypes():
+    """Callers of the reference do ``.to(device)`` / ``.eval()``; a dtype cast cannot be honoured by the drop-in (bf16 / fp32
+    inside libagb, fp32 at the boundary) and must raise instead of being ignored."""
+    import pytest
+    import torch
+    import affectgpt_b200 as agb
+    enc = agb.CLIP_VIT_LARGE(model_dir="")
+    assert enc.to("cuda:0") is enc and enc.to(torch.device("cpu")) is enc and enc.eval() is enc
+    assert enc.to(torch.float32) is enc and enc.float() is enc and enc.to(device="cuda", dtype=torch.float32) is enc
+    for bad in (lambda: enc.to(torch.float16), lambda: enc.half(), lambda: enc.bfloat16(), lambda: enc.double(),
+                lambda: enc.to("cuda:0", torch.bfloat16), lambda: enc.to(dtype=torch.float16),
+                lambda: enc.to(torch.zeros(1, dtype=torch.float16))):
+        with pytest.raises(TypeError):
+            bad()
+    aud = agb.HUBERT_LARGE(model_dir="")
+    with pytest.raises(TypeError):
+        aud.half()
