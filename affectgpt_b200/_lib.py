@@ -21,7 +21,8 @@ class AgbCfg(C.Structure):
         ("vit_layers", C.c_int32), ("hubert_layers", C.c_int32), ("hubert_conv_norm", C.c_int32),
         ("hubert_do_normalize", C.c_int32), ("llm_dim", C.c_int32), ("max_frames_per_chunk", C.c_int32),
         ("max_segments_per_chunk", C.c_int32), ("qf_video_queries", C.c_int32), ("qf_audio_queries", C.c_int32),
-        ("qf_multi_queries", C.c_int32), ("vit_dense_last_block", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("qf_multi_queries", C.c_int32), ("vit_dense_last_block", C.c_int32), ("hubert_post_layer_norm", C.c_int32),
+        ("hubert_no_feat_proj_ln", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 

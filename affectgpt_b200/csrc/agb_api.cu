@@ -242,8 +242,10 @@ int register_weights(agb_ctx* c) {
       if (int r = reg_f32(c, p + "layer_norm.bias", {512}, &c->h_conv_be[i])) return r;
     }
   }
-  if (int r = reg_f32(c, H + "feature_projection.layer_norm.weight", {512}, &c->h_fp_g)) return r;
-  if (int r = reg_f32(c, H + "feature_projection.layer_norm.bias", {512}, &c->h_fp_b)) return r;
+  if (!c->cfg.hubert_no_feat_proj_ln) {
+    if (int r = reg_f32(c, H + "feature_projection.layer_norm.weight", {512}, &c->h_fp_g)) return r;
+    if (int r = reg_f32(c, H + "feature_projection.layer_norm.bias", {512}, &c->h_fp_b)) return r;
+  }
   if (int r = dev_alloc(c, &c->h_fp_w, 1024ull * 512)) return r;
   reg_bf16_rows(c, H + "feature_projection.projection.weight", {1024, 512}, c->h_fp_w, 1024, 512, 512, 512);
   if (int r = reg_f32(c, H + "feature_projection.projection.bias", {1024}, &c->h_fp_bias)) return r;
@@ -554,6 +556,46 @@ int clip_chunk(agb_ctx* c, const void* frames, int in_dtype, int64_t F, float* o
   return gemm_bf16(g, s);
 }
 
+// do_stable_layer_norm = false: HF HubertEncoder + HubertEncoderLayer (modeling_hubert.py).  The residual stream is
+// normalised AFTER every sub-layer:  h0 = LN_enc(x + posconv(x));  a = h + out(MHA(h));  h' = LN(a);  f = h' + FFN(h');
+// h = LN_final(f).  hidden_states[l] = the stream entering layer l (already normalised), hidden_states[L] = the last layer's
+// output - no extra LayerNorm at the end.  Same kernels as the pre-LN block: the residual GEMMs += into the fp32 stream,
+// the LayerNorm then rewrites that stream in place (fp32) and emits the bf16 operand of the next GEMM.
+int hubert_post_ln_encoder(agb_ctx* c, int64_t G, float* out, cudaStream_t s) {
+  const int64_t M = G * 100;
+  const int L = c->cfg.hubert_layers;
+  if (int r = layernorm_f32_in(c->h_resid, 1024, M, 1024, c->h_enc_g, c->h_enc_b, 1e-5f, c->h_xln, 1024, c->h_resid, 1024, s)) return r;
+  bool first_pool = true;
+  for (int l = 0; l < L; ++l) {
+    const EncLayerW& W = c->h_layers[l];
+    if (l >= L - 3) {  // hidden_states[-4], [-3], [-2]
+      if (int r = seq_mean_pool(c->h_resid, (int)G, 100, 99, nullptr, nullptr, 0.f, 0.25f, first_pool ? 0 : 1, out, s)) return r;
+      first_pool = false;
+    }
+    GemmArgs g;
+    g.A = c->h_xln; g.lda = 1024; g.W = W.wqkv; g.M = (int)M; g.N = 3072; g.K = 1024; g.bias = W.bqkv;
+    g.out_bf16 = c->h_qkv; g.ld_bf16 = 3072;
+    if (int r = gemm_bf16(g, s)) return r;
+    if (int r = attention_mha16x64(c->h_qkv, c->h_attn, (int)G, 100, 99, 0.125f, s)) return r;
+    g = GemmArgs();
+    g.A = c->h_attn; g.lda = 1024; g.W = W.wo; g.M = (int)M; g.N = 1024; g.K = 1024; g.bias = W.bo;
+    g.res = c->h_resid; g.ld_res = 1024; g.out_f32 = c->h_resid; g.ld_f32 = 1024;
+    if (int r = gemm_bf16(g, s)) return r;
+    if (int r = layernorm_f32_in(c->h_resid, 1024, M, 1024, W.lnA_g, W.lnA_b, 1e-5f, c->h_xln, 1024, c->h_resid, 1024, s)) return r;
+    g = GemmArgs();
+    g.A = c->h_xln; g.lda = 1024; g.W = W.w1; g.M = (int)M; g.N = 4096; g.K = 1024; g.bias = W.b1; g.act = ACT_GELU_ERF;
+    g.out_bf16 = c->h_h1; g.ld_bf16 = 4096;
+    if (int r = gemm_bf16(g, s)) return r;
+    g = GemmArgs();
+    g.A = c->h_h1; g.lda = 4096; g.W = W.w2; g.M = (int)M; g.N = 1024; g.K = 4096; g.bias = W.b2;
+    g.res = c->h_resid; g.ld_res = 1024; g.out_f32 = c->h_resid; g.ld_f32 = 1024;
+    if (int r = gemm_bf16(g, s)) return r;
+    if (int r = layernorm_f32_in(c->h_resid, 1024, M, 1024, W.lnB_g, W.lnB_b, 1e-5f, c->h_xln, 1024, c->h_resid, 1024, s)) return r;
+    tap(c, "hubert.block" + std::to_string(l), c->h_resid, M * 1024 * 4, s);
+  }
+  return seq_mean_pool(c->h_resid, (int)G, 100, 99, nullptr, nullptr, 0.f, 0.25f, 1, out, s);   // hidden_states[-1]
+}
+
 int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t spg, float* out, cudaStream_t s) {
   const bool layer_norm = c->cfg.hubert_conv_norm == 0;
   // conv0 (+norm +GELU) -> c0 [G*6400, 512]
@@ -578,8 +620,12 @@ int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t 
   }
   const int64_t M = G * 100;
   tap(c, "hubert.conv", src, M * 512 * 2, s);
-  // feature projection: LN(512) -> Linear 512->1024 (fp32 residual stream + bf16 copy for the pos-conv)
-  if (int r = layernorm512_bf16_gelu(src, M, c->h_fp_g, c->h_fp_b, 1e-5f, false, dst, s)) return r;
+  // feature projection: [LN(512) ->] Linear 512->1024 (fp32 residual stream + bf16 copy for the pos-conv)
+  if (!c->cfg.hubert_no_feat_proj_ln) {
+    if (int r = layernorm512_bf16_gelu(src, M, c->h_fp_g, c->h_fp_b, 1e-5f, false, dst, s)) return r;
+  } else {
+    dst = src;                                                  // feat_proj_layer_norm = false (modeling_hubert.py, HubertFeatureProjection)
+  }
   GemmArgs g;
   g.A = dst; g.lda = 512; g.W = c->h_fp_w; g.M = (int)M; g.N = 1024; g.K = 512; g.bias = c->h_fp_bias;
   g.out_f32 = c->h_resid; g.ld_f32 = 1024;
@@ -596,6 +642,7 @@ int hubert_chunk(agb_ctx* c, const float* wav, int64_t seg0, int64_t G, int64_t 
   const int L = c->cfg.hubert_layers;
   bool first_pool = true;
   bool flip = true;
+  if (c->cfg.hubert_post_layer_norm) return hubert_post_ln_encoder(c, G, out, s);
   AGB_CHECK_CUDA(cudaMemsetAsync(c->h_lncnt, 0, (size_t)(M / 256 + 2) * sizeof(int), s));
   {                        // LayerNorm of the first block; every later one is emitted by the preceding FC2
     const EncLayerW& L0 = c->h_layers[0];

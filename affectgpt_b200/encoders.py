@@ -160,7 +160,8 @@ class HUBERT_LARGE(_EncoderBase):
     family = "hubert"
 
     def __init__(self, model_dir: Optional[str] = None, num_layers: int = 24, feat_extract_norm: str = "layer",
-                 do_normalize: bool = True, norm_scope: str = "clip", engine_cfg: Optional[dict] = None):
+                 do_normalize: bool = True, norm_scope: str = "clip", engine_cfg: Optional[dict] = None,
+                 do_stable_layer_norm: bool = True, feat_proj_layer_norm: bool = True):
         """``norm_scope``: "clip" -- zero-mean/unit-variance statistics per clip (its t segments), which is what
         the reference computes at batch size 1, its only call pattern; "batch" -- jointly over the whole call,
         which reproduces the reference bit-for-bit in intent when it is fed b > 1."""
@@ -173,6 +174,10 @@ class HUBERT_LARGE(_EncoderBase):
         self._engine_cfg.setdefault("hubert_layers", num_layers)
         self._engine_cfg.setdefault("feat_extract_norm", feat_extract_norm)
         self._engine_cfg.setdefault("do_normalize", do_normalize)
+        # HubertConfig switches of the 1024-wide architecture (encoder.py:403 loads whatever config.json says):
+        # do_stable_layer_norm (pre-LN blocks, hubert-large family) vs post-LN blocks; feat_proj_layer_norm; conv_bias
+        self._engine_cfg.setdefault("do_stable_layer_norm", do_stable_layer_norm)
+        self._engine_cfg.setdefault("feat_proj_layer_norm", feat_proj_layer_norm)
         model_dir = model_dir if model_dir is not None else config.PATH_TO_AUDIO.get("HUBERT_LARGE")
         if model_dir and os.path.isdir(model_dir):
             cfg = _read_json(os.path.join(model_dir, "config.json"))
@@ -181,11 +186,25 @@ class HUBERT_LARGE(_EncoderBase):
                 self._engine_cfg["hubert_layers"] = int(cfg["num_hidden_layers"])
             if cfg.get("feat_extract_norm"):
                 self._engine_cfg["feat_extract_norm"] = cfg["feat_extract_norm"]
-            if cfg and not cfg.get("do_stable_layer_norm", True):
-                raise NotImplementedError("only the stable-layer-norm (hubert-large) encoder variant is implemented")
+            if cfg:
+                if (cfg.get("hidden_size", 1024), cfg.get("num_attention_heads", 16), cfg.get("intermediate_size", 4096)) != (1024, 16, 4096):
+                    raise NotImplementedError("HUBERT_LARGE kernels are built for hidden 1024 / 16 heads / FFN 4096 "
+                                              f"(got {cfg.get('hidden_size')}/{cfg.get('num_attention_heads')}/{cfg.get('intermediate_size')})")
+                self._engine_cfg["do_stable_layer_norm"] = bool(cfg.get("do_stable_layer_norm", False))
+                self._engine_cfg["feat_proj_layer_norm"] = bool(cfg.get("feat_proj_layer_norm", True))
             if "do_normalize" in pre:
                 self._engine_cfg["do_normalize"] = bool(pre["do_normalize"])
-            self._state = _read_checkpoint(model_dir)
+            self.load_hf_state_dict(_read_checkpoint(model_dir))
+
+    def load_hf_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """conv_bias = false checkpoints carry no conv biases (HubertConfig.conv_bias): the kernels add a bias vector in
+        every conv epilogue, so a missing one is filled with zeros - same result."""
+        sd = dict(state_dict)
+        for i in range(7):
+            w, b = f"feature_extractor.conv_layers.{i}.conv.weight", f"feature_extractor.conv_layers.{i}.conv.bias"
+            if w in sd and b not in sd:
+                sd[b] = torch.zeros(sd[w].shape[0], dtype=torch.float32, device=sd[w].device)
+        super().load_hf_state_dict(sd)
 
     # audio: [b, t, 1, 128, 204] mel (ignored); raw_audio: [b, t, 1, 32000]   (encoder.py:416-432)
     @torch.no_grad()

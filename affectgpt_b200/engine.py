@@ -31,7 +31,8 @@ class Engine:
     def __init__(self, device="cuda:0", vit_layers: int = 24, hubert_layers: int = 24,
                  feat_extract_norm: str = "layer", do_normalize: bool = True, llm_dim: int = 3584,
                  max_frames_per_chunk: int = 512, max_segments_per_chunk: int = 512, qf_video_queries: int = 0,
-                 qf_audio_queries: int = 0, qf_multi_queries: int = 0, vit_dense_last_block: bool = False):
+                 qf_audio_queries: int = 0, qf_multi_queries: int = 0, vit_dense_last_block: bool = False,
+                 do_stable_layer_norm: bool = True, feat_proj_layer_norm: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("affectgpt_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if feat_extract_norm not in ("layer", "group"):
@@ -50,6 +51,8 @@ class Engine:
         cfg.hubert_do_normalize = 1 if do_normalize else 0
         cfg.llm_dim = llm_dim
         cfg.vit_dense_last_block = 1 if vit_dense_last_block else 0
+        cfg.hubert_post_layer_norm = 0 if do_stable_layer_norm else 1     # HubertConfig.do_stable_layer_norm
+        cfg.hubert_no_feat_proj_ln = 0 if feat_proj_layer_norm else 1     # HubertConfig.feat_proj_layer_norm
         cfg.max_frames_per_chunk = max_frames_per_chunk
         cfg.max_segments_per_chunk = max_segments_per_chunk
         cfg.qf_video_queries, cfg.qf_audio_queries, cfg.qf_multi_queries = qf_video_queries, qf_audio_queries, qf_multi_queries

@@ -297,15 +297,18 @@ def build_path(clip_state: Dict[str, torch.Tensor], hubert_state: Dict[str, torc
                fusion_state: Dict[str, torch.Tensor], device="cuda:0", vit_layers: int = 24, hubert_layers: int = 24,
                feat_extract_norm: str = "layer", do_normalize: bool = True, norm_scope: str = "clip",
                llm_dim: int = config.LLM_DIM, max_frames_per_chunk: int = 512,
-               max_segments_per_chunk: int = 512) -> AffectGPTFusion:
+               max_segments_per_chunk: int = 512, do_stable_layer_norm: bool = True,
+               feat_proj_layer_norm: bool = True) -> AffectGPTFusion:
     """One engine, both encoders and the fusion heads on ``device`` from in-memory state dicts."""
     eng = Engine(device, vit_layers=vit_layers, hubert_layers=hubert_layers, feat_extract_norm=feat_extract_norm,
                  do_normalize=do_normalize, llm_dim=llm_dim, max_frames_per_chunk=max_frames_per_chunk,
-                 max_segments_per_chunk=max_segments_per_chunk)
+                 max_segments_per_chunk=max_segments_per_chunk, do_stable_layer_norm=do_stable_layer_norm,
+                 feat_proj_layer_norm=feat_proj_layer_norm)
     vis = CLIP_VIT_LARGE(model_dir="", num_layers=vit_layers)
     vis.load_hf_state_dict(clip_state)
     aud = HUBERT_LARGE(model_dir="", num_layers=hubert_layers, feat_extract_norm=feat_extract_norm,
-                       do_normalize=do_normalize, norm_scope=norm_scope)
+                       do_normalize=do_normalize, norm_scope=norm_scope, do_stable_layer_norm=do_stable_layer_norm,
+                       feat_proj_layer_norm=feat_proj_layer_norm)
     aud.load_hf_state_dict(hubert_state)
     model = AffectGPTFusion(vis, aud, llm_dim=llm_dim, engine=eng)
     model.load_state_dict(fusion_state)

@@ -44,7 +44,12 @@ typedef struct agb_cfg {
   int32_t qf_multi_queries;       /* num_multi_query_token when multi_fusion_type == "qformer", else 0 */
   int32_t vit_dense_last_block;   /* 0 (default): the last ViT block computes only what the pooled CLS row needs (K/V for all
                                      tokens, everything else for the CLS row); 1: all 257 rows, as the reference does */
-  int32_t reserved[5];
+  int32_t hubert_post_layer_norm; /* 0 (default): do_stable_layer_norm = true, pre-LN blocks (hubert-large family,
+                                     HF HubertEncoderStableLayerNorm, modeling_hubert.py); 1: do_stable_layer_norm = false,
+                                     post-LN blocks with encoder.layer_norm in front of the stack (HF HubertEncoder /
+                                     HubertEncoderLayer) */
+  int32_t hubert_no_feat_proj_ln; /* 0 (default): feat_proj_layer_norm = true; 1: the projection reads the raw conv features */
+  int32_t reserved[3];
 } agb_cfg;
 
 enum { AGB_DTYPE_F32 = 0, AGB_DTYPE_U8 = 1, AGB_DTYPE_BF16 = 2 };

@@ -57,17 +57,19 @@ def build_clip_vision(num_layers: int = 24, seed: int = 1234):
     return model
 
 
-def build_hubert(num_layers: int = 24, feat_extract_norm: str = "layer", seed: int = 1234):
-    """HuBERT-large (stable-LN family) random init.  HF: models/hubert/modeling_hubert.py."""
+def build_hubert(num_layers: int = 24, feat_extract_norm: str = "layer", seed: int = 1234,
+                 do_stable_layer_norm: bool = True, conv_bias: bool = True, feat_proj_layer_norm: bool = True):
+    """HuBERT at the large width, random init.  HF: models/hubert/modeling_hubert.py.  Defaults = the hubert-large family
+    (stable / pre-LN blocks); do_stable_layer_norm=False selects HubertEncoder / HubertEncoderLayer (post-LN)."""
     from transformers import HubertConfig, HubertModel
 
     torch.manual_seed(seed)
     cfg = HubertConfig(
         hidden_size=1024, num_hidden_layers=num_layers, num_attention_heads=16,
-        intermediate_size=4096, feat_extract_norm=feat_extract_norm, do_stable_layer_norm=True,
-        conv_bias=True, num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16,
+        intermediate_size=4096, feat_extract_norm=feat_extract_norm, do_stable_layer_norm=do_stable_layer_norm,
+        conv_bias=conv_bias, num_conv_pos_embeddings=128, num_conv_pos_embedding_groups=16,
         conv_dim=(512,) * 7, conv_stride=(5, 2, 2, 2, 2, 2, 2), conv_kernel=(10, 3, 3, 3, 3, 2, 2),
-        feat_proj_layer_norm=True, layer_norm_eps=1e-5, hidden_act="gelu",
+        feat_proj_layer_norm=feat_proj_layer_norm, layer_norm_eps=1e-5, hidden_act="gelu",
         feat_extract_activation="gelu",
     )
     model = HubertModel(cfg).eval()

@@ -114,6 +114,36 @@ def test_hubert_small_with_taps_and_golden(norm):
     eng.close()
 
 
+@pytest.mark.parametrize("norm,conv_bias,fp_ln", [("layer", True, True), ("group", False, False), ("group", True, True)])
+def test_hubert_post_layer_norm_encoder(norm, conv_bias, fp_ln):
+    """do_stable_layer_norm = false: HF HubertEncoder / HubertEncoderLayer (post-LN blocks, encoder.layer_norm in front of
+    the stack, no LayerNorm after it) - what a base-family config.json selects, together with feat_extract_norm='group',
+    conv_bias=false and feat_proj_layer_norm=false.  Same gate, per-block taps (hidden_states[l+1] = output of layer l)."""
+    import affectgpt_b200 as agb
+    hub = R.build_hubert(num_layers=4, feat_extract_norm=norm, seed=2468, do_stable_layer_norm=False, conv_bias=conv_bias,
+                         feat_proj_layer_norm=fp_ln)
+    sd = hub.state_dict()
+    assert ("feature_extractor.conv_layers.1.conv.bias" in sd) == conv_bias
+    assert ("feature_projection.layer_norm.weight" in sd) == fp_ln
+    eng = agb.Engine(DEV, vit_layers=2, hubert_layers=4, feat_extract_norm=norm, do_stable_layer_norm=False,
+                     feat_proj_layer_norm=fp_ln)
+    enc = agb.HUBERT_LARGE(model_dir="", num_layers=4, feat_extract_norm=norm, do_stable_layer_norm=False,
+                           feat_proj_layer_norm=fp_ln)
+    enc.load_hf_state_dict(sd)
+    enc.attach_engine(eng)
+    raw = R.synth_audio(1, 3, seed=13)
+    taps = {n: eng.tap(n, (3 * 100, 1024)) for n in ("hubert.block0", "hubert.block3")}
+    got = enc(None, raw.to(DEV))
+    eng.clear_taps()
+    want, hs = R.hubert_large_forward(hub, raw, return_hidden_states=True)
+    assert len(hs) == 5
+    gate(taps["hubert.block0"].reshape(3, 100, 1024)[:, :99], hs[1], f"post-LN[{norm}] hubert.block0")
+    gate(taps["hubert.block3"].reshape(3, 100, 1024)[:, :99], hs[4], f"post-LN[{norm}] hubert.block3")
+    gate(got, want, f"post-LN[{norm}, conv_bias={conv_bias}, feat_proj_ln={fp_ln}] features")
+    assert R.nn_identity(got[0].cpu(), want[0])
+    eng.close()
+
+
 def test_hubert_norm_scope_batch_vs_clip(small_path):
     """b=2: per-clip statistics (reference at b=1 per clip) vs joint statistics (reference fed b=2) -- SURVEY F3."""
     import affectgpt_b200 as agb
