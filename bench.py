@@ -346,10 +346,13 @@ def main():
         e0.record()
         for _ in range(k):
             fn()
+        ec = torch.cuda.Event(enable_timing=True)
+        ec.record()                              # this rank's own kernels are done here (the gathers run on a side stream)
         drain()                                  # the last step's gather is part of the timed region
         e1.record()
         barrier()
         own_ms[tag] = e0.elapsed_time(e1)
+        own_ms[tag + "_compute"] = e0.elapsed_time(ec)
         ms = torch.tensor([own_ms[tag]], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -395,11 +398,14 @@ def main():
         flag = torch.tensor([1 if (same and mine) else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         parity = bool(int(flag))
-        rows = torch.tensor([own_ms["resident"] / args.steps, own_ms["e2e"] / args.steps, float((clk or {}).get("sm_mhz") or 0.0)], device=dev)
+        rows = torch.tensor([own_ms["resident"] / args.steps, own_ms["e2e"] / args.steps, float((clk or {}).get("sm_mhz") or 0.0),
+                             own_ms["resident_compute"] / args.steps], device=dev)
         allr = [torch.empty_like(rows) for _ in range(world)]
         dist.all_gather(allr, rows)
-        per_rank = {"ms_per_step": [round(float(r[0]), 3) for r in allr], "e2e_ms_per_step": [round(float(r[1]), 3) for r in allr],
-                    "sm_mhz": [float(r[2]) for r in allr], "slowest_rank": int(max(range(world), key=lambda i: float(allr[i][0])))}
+        per_rank = {"ms_per_step": [round(float(r[0]), 3) for r in allr],
+                    "own_kernels_ms_per_step": [round(float(r[3]), 3) for r in allr],      # before waiting for the last gather
+                    "e2e_ms_per_step": [round(float(r[1]), 3) for r in allr],
+                    "sm_mhz": [float(r[2]) for r in allr], "slowest_rank": int(max(range(world), key=lambda i: float(allr[i][3])))}
 
     # instrumented pass: CUDA-event pairs around every kernel wrapper (separate from the timed value)
     barrier()
