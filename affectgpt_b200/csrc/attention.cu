@@ -201,7 +201,6 @@ int attention_mha16x64(const bf16* qkv, bf16* out, int nseq, int seq_stride, int
     const int r = attention_tc2(qkv, out, nseq, seq_stride, seq_valid, scale, s, reverse);
     if (r >= 0) return r;
   }
-  if (seq_valid <= 112) return launch_mha<7>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   if (seq_valid <= 272) return launch_mha<17>(qkv, out, nseq, seq_stride, seq_valid, scale, s);
   AGB_REQUIRE(false, "attention: sequence length > 272 not supported by the register-resident softmax kernel");
 }

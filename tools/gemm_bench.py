@@ -1,5 +1,5 @@
 """Micro-benchmark of the tcgen05 GEMM on the path's shapes (CUDA events, L2 flushed between iterations by cycling
-through operand sets larger than the 126 MB L2).  AGB_GEMM_CTA_GROUP=1 forces single-CTA tiles."""
+through operand sets larger than the 126 MB L2)."""
 import json
 import os
 import sys
@@ -59,7 +59,7 @@ for name, M, N, K, act, resid in shapes:
           f"{2.0 * M * N * K / ms_lib / 1e9:.0f} TFLOP/s", flush=True)
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 os.makedirs(out, exist_ok=True)
-json.dump(res, open(os.path.join(out, f"gemm_bench_cg{os.environ.get('AGB_GEMM_CTA_GROUP', '2')}.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(out, "gemm_vs_cublas.json"), "w"), indent=1)
 
 # grouped positional conv (k = 128, 16 groups of 64): 512 sequences of 99 frames, resid += gelu(conv)
 nseq, stride, valid = 512, 100, 99
