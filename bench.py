@@ -58,9 +58,9 @@ def read_peaks():
 
 def gemm_traffic_per_launch():
     """Mean DRAM bytes (read + write) per GEMM launch of one C2 step, from the committed ncu launch list
-    (profiles/r01_traffic.json, produced by tools/summarize_launches.py from an ncu capture of this very command);
+    (profiles/r02_traffic.json, produced by tools/summarize_launches.py from an ncu capture of this very command);
     None when no capture has been committed."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return float(json.load(open(p))["gemm_kernel"]["dram_bytes_per_launch"])
     except Exception:
@@ -92,17 +92,18 @@ class ClockSampler:
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, watts = [], 0, set(), []
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                watts.append(float(r[3]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w": statistics.median(watts) if watts else None}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
