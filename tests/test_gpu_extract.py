@@ -112,3 +112,46 @@ def test_batched_sweep_files_equal_per_sample_sweep_bit_for_bit(tmp_path):
     assert sorted(trees[0]) == sorted(trees[1]) and len(trees[0]) == 4 * 5 + 1
     for k in trees[0]:
         assert np.array_equal(trees[0][k], trees[1][k]), k
+
+
+def test_emotion_peak_sweep_follows_the_extractor_not_load_video(tmp_path):
+    """--frame_sampling emotion_peak: the reference extractor branches to extract_frame_features_smart
+    (extract_multimodal_features_precompute.py:174-175): AU json missing -> np.linspace(0, vlen - 1, 8) (:400-403), AU json
+    with a peak -> calculate_smart_frame_indices; never load_video's "middle frame repeated 8 times".  The file on disk must
+    be the features of exactly those frames."""
+    import json
+    import affectgpt_b200 as agb
+    from affectgpt_b200 import extract as X, sampling
+    names = ["clipA", "clipB"]
+    data = _write_dataset(tmp_path, names)
+    mer = tmp_path / "mer_factory"
+    (mer / "clipB").mkdir(parents=True)
+    vlen_b = len(data["clipB"][0])
+    au = {"total_frames": vlen_b, "peak_frames": [{"peak_index": 9, "frames_before_peak": 3, "frames_after_peak": 3}]}
+    (mer / "clipB" / "clipB_au_analysis.json").write_text(json.dumps({"au_info": au}))
+    clip = R.build_clip_vision(num_layers=2, seed=1234)
+    hub = R.build_hubert(num_layers=3, feat_extract_norm="layer", seed=1234)
+    model = agb.build_path(clip.state_dict(), hub.state_dict(), R.build_fusion_state(seed=1234), device=DEV, vit_layers=2,
+                           hubert_layers=3)
+    ex = X.MultimodalFeatureExtractor(model.visual_encoder, model.acoustic_encoder, model, device=DEV,
+                                      mer_factory_output=str(mer))
+    args = X.build_parser().parse_args([
+        "--dataset", "mer2024", "--modality", "frame", "--video_root", str(tmp_path / "video"), "--sample_list",
+        str(tmp_path / "names.txt"), "--save_root", str(tmp_path / "out"), "--quiet", "--frame_sampling", "emotion_peak",
+        "--mer-factory-output", str(mer)])
+    X.validate_args(args)
+    X.run_sweep(args, ex, names, log=lambda *_: None)
+    out = tmp_path / "out" / "mer2024" / "frame_CLIP_VIT_LARGE_emotion_peak_8frms"
+    want_idx = {"clipA": sorted(np.linspace(0, len(data["clipA"][0]) - 1, 8).astype(int).tolist()),      # no AU json
+                "clipB": OS.smart_frame_indices(au, vlen_b)}
+    assert want_idx["clipB"] == sampling.smart_frame_indices(au, vlen_b) and len(set(want_idx["clipA"])) == 8
+    for n in names:
+        frames = data[n][0]
+        raw = torch.from_numpy(frames[want_idx[n]]).permute(3, 0, 1, 2).float()[None]
+        want = R.clip_vit_large_forward(clip, raw)[0]
+        got = np.load(out / f"{n}.npy")
+        assert got.shape == (8, 768)
+        gate(torch.from_numpy(got), want, f"emotion_peak frame features {n}")
+        mid = torch.from_numpy(frames[[len(frames) // 2] * 8]).permute(3, 0, 1, 2).float()[None]
+        wrong = R.clip_vit_large_forward(clip, mid)[0]                    # what load_video's rule would have produced
+        assert float((torch.from_numpy(got) - wrong).abs().max()) > 10 * float((torch.from_numpy(got) - want).abs().max())
