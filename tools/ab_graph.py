@@ -16,11 +16,23 @@ ap.add_argument("--clips", type=int, default=64)
 ap.add_argument("--rounds", type=int, default=12)
 args = ap.parse_args()
 DEV = "cuda:0"
-model = agb.build_path(S.clip_state(24, DEV), S.hubert_state(24, "layer", DEV), S.fusion_state(3584, DEV), device=DEV)
+_models = {}
+
+
+def model_for(chunk):
+    """One engine per workspace chunking (pseudo-setting CHUNK=<frames>x<segments>; default 512x512)."""
+    if chunk not in _models:
+        f, sgm = (int(x) for x in chunk.split("x"))
+        _models[chunk] = agb.build_path(S.clip_state(24, DEV), S.hubert_state(24, "layer", DEV), S.fusion_state(3584, DEV),
+                                        device=DEV, max_frames_per_chunk=f, max_segments_per_chunk=sgm)
+    return _models[chunk]
+
+
 fr, au = S.frames(args.clips, 8, seed=1).to(DEV), S.audio(args.clips, 8, seed=2).to(DEV)
 arms = []
 for setting in args.settings:
     kv = dict(x.split("=", 1) for x in setting.split(",") if x)
+    model = model_for(kv.pop("CHUNK", "512x512"))
     old = {k: os.environ.get(k) for k in kv}
     os.environ.update(kv)
     g = agb.GraphedClipBatch(model, args.clips, 8, 8, device=DEV)
