@@ -1,4 +1,4 @@
-"""Micro-benchmark of the attention kernels on the path's shapes (CUDA events).  AGB_ATTENTION=hmma forces mma.sync."""
+"""Micro-benchmark of the attention kernels on the path's shapes (CUDA events)."""
 import os
 import sys
 
