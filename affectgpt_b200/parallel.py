@@ -27,6 +27,30 @@ def shard_sizes(num_clips: int, world_size: int) -> List[int]:
     return [len(range(r, num_clips, world_size)) for r in range(world_size)]
 
 
+def balanced_counts(num_clips: int, speeds: Sequence[float], max_shift: Optional[int] = None) -> List[int]:
+    """Split ``num_clips`` over the ranks in proportion to their measured speed (clips per second, any unit).
+
+    The GPUs of one node do not run at one speed: every B200 sits at its own point of the 1 kW power cap (SM clocks of
+    1.26-1.42 GHz were seen on one box), and with equal shards the job runs at the pace of the slowest one.  Largest-
+    remainder rounding; ``max_shift`` bounds how far a rank's share may move from the even split (None = unbounded).
+    Deterministic for given speeds, so every rank computes the same list from the all-gathered speeds."""
+    w = len(speeds)
+    if w == 0 or any(not (s > 0) for s in speeds):
+        raise ValueError("speeds must be positive")
+    tot = float(sum(speeds))
+    even = num_clips / w
+    ideal = [num_clips * s / tot for s in speeds]
+    if max_shift is not None:
+        ideal = [min(max(x, even - max_shift), even + max_shift) for x in ideal]
+        scale = num_clips / sum(ideal)
+        ideal = [x * scale for x in ideal]
+    counts = [int(x) for x in ideal]
+    order = sorted(range(w), key=lambda i: (-(ideal[i] - counts[i]), i))
+    for i in order[: num_clips - sum(counts)]:
+        counts[i] += 1
+    return counts
+
+
 def _all_gather_flat(recv: torch.Tensor, send: torch.Tensor, group) -> None:
     """recv [W * n] <- every rank's send [n] (rank-major)."""
     dist.all_gather_into_tensor(recv, send, group=group)
@@ -45,14 +69,23 @@ class ClipGather:
     first one on the side stream and reuses the buffers: ``wait`` then returns the latest result.  On CPU tensors (gloo)
     everything runs synchronously."""
 
-    def __init__(self, num_clips: int, row_shape: Sequence[int], dtype: torch.dtype, device, group=None):
+    def __init__(self, num_clips: int, row_shape: Sequence[int], dtype: torch.dtype, device, group=None,
+                 counts: Optional[Sequence[int]] = None):
+        """Default sharding: strided (clip i on rank i % W).  With ``counts`` (e.g. from ``balanced_counts``) rank r holds
+        the contiguous block of ``counts[r]`` clips that starts at ``sum(counts[:r])``."""
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("ClipGather needs an initialised process group")
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.num_clips = int(num_clips)
-        self.sizes = shard_sizes(self.num_clips, self.world)
+        if counts is not None:
+            if len(counts) != self.world or sum(counts) != self.num_clips or min(counts) < 0:
+                raise ValueError(f"counts {list(counts)} do not split {self.num_clips} clips over {self.world} ranks")
+            self.sizes = [int(c) for c in counts]
+        else:
+            self.sizes = shard_sizes(self.num_clips, self.world)
+        self.contiguous = counts is not None
         self.pad = max(self.sizes) if self.sizes else 0
         self.row_shape = tuple(int(d) for d in row_shape)
         dev = torch.device(device)
@@ -62,6 +95,13 @@ class ClipGather:
         # clip i = j * W + r sits at recv[r, j]: viewed as [pad, W, ...] the output is one strided copy of recv^T;
         # the padding rows of uneven shards all land behind row num_clips
         self.out_padded = torch.empty((self.pad * self.world,) + self.row_shape, dtype=dtype, device=dev)
+        self.index = None
+        if self.contiguous:                                     # clip i of rank r's block sits at recv[r, i - offset_r]
+            idx, off = [], 0
+            for r, n in enumerate(self.sizes):
+                idx.extend(r * self.pad + j for j in range(n))
+                off += n
+            self.index = torch.tensor(idx, dtype=torch.int64, device=dev)
         self.cuda = dev.type == "cuda"
         if self.cuda:
             self.stream = torch.cuda.Stream(device=dev)
@@ -89,7 +129,11 @@ class ClipGather:
     def _run(self, local_rows: torch.Tensor) -> None:
         self.send[: self.sizes[self.rank]].copy_(local_rows, non_blocking=True)
         _all_gather_flat(self.recv.view(-1), self.send.view(-1), self.group)
-        self.out_padded.view((self.pad, self.world) + self.row_shape).copy_(self.recv.transpose(0, 1), non_blocking=True)
+        if self.contiguous:
+            torch.index_select(self.recv.view((self.world * self.pad,) + self.row_shape), 0, self.index,
+                               out=self.out_padded[: self.num_clips])
+        else:
+            self.out_padded.view((self.pad, self.world) + self.row_shape).copy_(self.recv.transpose(0, 1), non_blocking=True)
 
     def wait(self) -> torch.Tensor:
         if not self._pending:

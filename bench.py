@@ -232,6 +232,9 @@ def main():
     ap.add_argument("--cpu-clips", type=int, default=2, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the HF-modules-on-this-GPU comparator (N = 1)")
+    ap.add_argument("--balance", action="store_true",
+                    help="N > 1: shares of the global batch proportional to each GPU's measured speed instead of equal shards "
+                         "(parallel.balanced_counts; opt-in, see the comment at the calibration)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel separately instead of replaying a CUDA graph")
     ap.add_argument("--only-resident", action="store_true",
                     help="profiling aid (tools/launch_list.sh): run the warm-up and the device-resident timed steps only")
@@ -253,23 +256,60 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
-    B = args.clips
+    B_nominal = args.clips                       # clips per GPU of the workload; the global batch is B_nominal * world
+    B = B_nominal
 
-    model = agb.build_path(S.clip_state(24, dev), S.hubert_state(24, "layer", dev), S.fusion_state(3584, dev), device=dev,
-                           max_frames_per_chunk=512, max_segments_per_chunk=512)
-    # host (pinned) and device copies of this rank's batch; frames fp32 0..255 as the reference passes them
     NF, NS, FACES = args.n_frames, args.n_segments, args.with_faces
+    B_max = B_nominal + (max(B_nominal // 8, 1) if world > 1 and args.balance else 0)            # largest balanced share
+    model = agb.build_path(S.clip_state(24, dev), S.hubert_state(24, "layer", dev), S.fusion_state(3584, dev), device=dev,
+                           max_frames_per_chunk=max(512, B_max * NF), max_segments_per_chunk=max(512, B_max * NS))
     fof = "multiface_audio_face_frame_text" if FACES else "multiframe_audio_frame_text"
+    total_clips = B_nominal * world
+
+    # ---- N > 1: shares of the global batch in proportion to each GPU's measured speed.  The GPUs of a node sit at different
+    # points of the 1 kW power cap (SM clocks 1.26-1.42 GHz on one box) and equal shards run at the pace of the slowest.
+    # Calibration = the equal-shard step itself, timed per rank on its own stream; the tokens do not depend on which rank
+    # computes a clip (checked below: multi_gpu_parity), so only the split changes.  OPT-IN (--balance), because a static
+    # calibration is only as good as the speeds are stable: on one 8 x B200 box it gained 2.9 % (equal shards 4017 clips/s,
+    # own-kernel times 123.5-127.4 ms; balanced 4134, 121.9-123.8 ms, shares 62-66), on a 4-GPU run the GPU it had measured
+    # fastest was 3 % slower a few seconds later and the balanced split lost 1 % (2040 vs ~2060) - the power-cap operating
+    # point of a GPU drifts on the scale of seconds.  Calibration = 12 + 16 equal-shard steps per rank.
+    counts, calib = None, None
+    if world > 1 and args.balance and not args.no_graph:
+        g0 = agb.GraphedClipBatch(model, B_nominal, NF, NS, with_faces=FACES, device=dev)
+        g0.raw_frames.copy_(S.frames(B_nominal, NF, seed=1000 + rank).to(dev))
+        g0.raw_audios.copy_(S.audio(B_nominal, NS, seed=2000 + rank).to(dev))
+        if FACES:
+            g0.raw_faces.copy_(S.frames(B_nominal, NF, seed=3000 + rank).to(dev))
+        for _ in range(12):                      # ~1.5 s: past the boost budget a cold GPU starts with
+            g0()
+        dist.barrier()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(16):
+            g0()
+        c1.record()
+        torch.cuda.synchronize()
+        t_own = torch.tensor([c0.elapsed_time(c1) / 16], device=dev)
+        t_all = [torch.empty_like(t_own) for _ in range(world)]
+        dist.all_gather(t_all, t_own)
+        calib = [float(t) for t in t_all]
+        counts = P.balanced_counts(total_clips, [1.0 / t for t in calib], max_shift=max(B_nominal // 8, 1))
+        B = counts[rank]
+        del g0
+        torch.cuda.empty_cache()
+    offsets = [sum(counts[:r]) for r in range(world)] if counts is not None else None
+    # host (pinned) and device copies of this rank's batch; frames fp32 0..255 as the reference passes them
     h_frames = S.frames(B, NF, seed=1000 + rank).pin_memory()
     h_audio = S.audio(B, NS, seed=2000 + rank).pin_memory()
     h_faces = S.frames(B, NF, seed=3000 + rank).pin_memory() if FACES else None
     d_frames, d_audio = h_frames.to(dev), h_audio.to(dev)
     d_faces = h_faces.to(dev) if FACES else None
     h_tokens = torch.empty((B, 4 if FACES else 3, 3584), dtype=torch.float32).pin_memory()
-    total_clips = B * world
 
     n_tok = 4 if FACES else 3
-    gather = P.ClipGather(total_clips, (n_tok, 3584), torch.float32, dev) if world > 1 else None
+    gather = P.ClipGather(total_clips, (n_tok, 3584), torch.float32, dev, counts=counts) if world > 1 else None
 
     def finish(out):
         """This rank's fused tokens in prompt order [B, n_tok, 3584]; at N > 1 their all_gather is queued on the gather's
@@ -385,17 +425,19 @@ def main():
         last = step_resident()
         gathered = drain().clone()
         other = (rank + 1) % world
-        pick = [0, B - 1]
-        o_frames = S.frames(B, NF, seed=1000 + other)[pick].to(dev)
-        o_audio = S.audio(B, NS, seed=2000 + other)[pick].to(dev)
-        o_faces = S.frames(B, NF, seed=3000 + other)[pick].to(dev) if FACES else None
+        B_other = counts[other] if counts is not None else B
+        pick = [0, B_other - 1]
+        o_frames = S.frames(B_other, NF, seed=1000 + other)[pick].to(dev)
+        o_audio = S.audio(B_other, NS, seed=2000 + other)[pick].to(dev)
+        o_faces = S.frames(B_other, NF, seed=3000 + other)[pick].to(dev) if FACES else None
         smp = {"raw_frames": o_frames, "raw_audios": o_audio, "face_or_frame": fof}
         if FACES:
             smp["raw_faces"] = o_faces
         o = model.encode_clip_batch(smp)
         redo = torch.cat([o["multi"], o["audio"]] + ([o["face"]] if FACES else []) + [o["frame"]], dim=1)
-        same = torch.equal(redo, gathered[[j * world + other for j in pick]])
-        mine = torch.equal(gathered[rank::world], last)
+        rows_of = (lambda r, js: [offsets[r] + j for j in js]) if counts is not None else (lambda r, js: [j * world + r for j in js])
+        same = torch.equal(redo, gathered[rows_of(other, pick)])
+        mine = torch.equal(gathered[rows_of(rank, range(B))], last)
         flag = torch.tensor([1 if (same and mine) else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         parity = bool(int(flag))
@@ -425,7 +467,7 @@ def main():
     g = prof["gemm"]
     gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
     tf_per_clip = clip_tflop(NF, NS, FACES)
-    cfg = workload_config(B, world, NF, NS, FACES)
+    cfg = workload_config(B_nominal, world, NF, NS, FACES)
     step_tflops = value / world * cfg["tflop_per_clip_executed"]       # FLOPs that actually ran (pruned last ViT block)
     step_tflops_dense = value / world * tf_per_clip                     # SURVEY 8d dense figure, for comparison
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -466,6 +508,10 @@ def main():
         line["multi_gpu_parity_check"] = "each rank recomputed 2 clips of the next rank's shard at batch 2 (eager) and compared them, and its own rows, with the all_gathered tokens: torch.equal"
         line["per_rank"] = per_rank
         line["gather"] = "all_gather_into_tensor on a side stream (parallel.ClipGather), one per step, overlapped with the next step"
+        line["balance"] = ({"clips_per_rank": counts, "equal_shard_ms_per_step": [round(t, 3) for t in calib],
+                            "rule": "global batch of clips_per_gpu x N split in proportion to each GPU's measured equal-shard speed "
+                                    "(parallel.balanced_counts, +-1/8 of a shard at most; --balance)"}
+                           if counts is not None else {"clips_per_rank": [B_nominal] * world, "rule": "equal shards (default; --balance splits by measured speed)"})
     if rank == 0 and world == 1 and not args.no_library_baseline:
         try:
             line["library_gpu_baseline"] = library_gpu_baseline(B, NF, NS, dev)

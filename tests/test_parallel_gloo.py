@@ -18,6 +18,17 @@ def test_shard_indices_cover_all_clips_once():
             assert [len(p) for p in parts] == P.shard_sizes(n, w)
 
 
+def test_balanced_counts_follow_speed_and_sum_up():
+    assert P.balanced_counts(512, [1.0] * 8) == [64] * 8
+    c = P.balanced_counts(512, [544, 539, 525, 537, 536, 542, 537, 530])          # clips/s of one 8 x B200 box
+    assert sum(c) == 512 and c[0] == max(c) and c[2] == min(c) and max(c) - min(c) <= 4
+    c = P.balanced_counts(128, [1.0, 3.0], max_shift=8)
+    assert c == [56, 72]
+    assert P.balanced_counts(7, [1.0, 1.0, 1.0]) in ([3, 2, 2],)
+    with pytest.raises(ValueError):
+        P.balanced_counts(8, [1.0, 0.0])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -40,6 +51,12 @@ def _worker(rank, world, port, num_clips, q):
         for step in range(3):
             g.start(mine + step)
             ok = ok and bool(torch.equal(g.wait(), full + step))
+        # speed-balanced contiguous blocks (uneven on purpose)
+        counts = P.balanced_counts(num_clips, [1.0, 1.6])
+        off = sum(counts[:rank])
+        gb = P.ClipGather(num_clips, (4, 6), torch.float32, "cpu", counts=counts)
+        gb.start(full[off:off + counts[rank]].clone())
+        ok = ok and bool(torch.equal(gb.wait(), full)) and sum(counts) == num_clips
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
