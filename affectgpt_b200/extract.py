@@ -422,7 +422,7 @@ def run_sweep(args, extractor, sample_names: List[str], log=print) -> Dict[str, 
 
 
 def run_sweep_batched(args, extractor, sample_names: List[str], batch_size: int = 32, workers: int = 8,
-                      log=print) -> Dict[str, int]:
+                      log=print, claim: Optional[Callable[[], Optional[int]]] = None) -> Dict[str, int]:
     """Same files, same statistics and same per-sample failure rules as ``run_sweep``, but the device sees batches:
     a thread pool decodes and stages the next batch (and writes the previous one) while the GPU encodes, all frames and face crops of ``batch_size`` samples
     go through ONE ViT call and all their audio segments through ONE HuBERT call, and in ``--modality all`` the multi
@@ -508,7 +508,21 @@ def run_sweep_batched(args, extractor, sample_names: List[str], batch_size: int 
             writes.append(w)
         return writes, st
 
-    batches = [sample_names[i:i + batch_size] for i in range(0, len(sample_names), batch_size)]
+    # Batch source: this rank's own list cut into batches, or - ``claim`` given - batches of the GLOBAL list claimed one at
+    # a time from a counter all ranks share (dynamic sharding: a GPU that runs slower under the power cap simply claims
+    # fewer batches; samples are independent and the encoders batch-invariant, so the files do not depend on who wrote them).
+    if claim is None:
+        batch_iter = iter([sample_names[i:i + batch_size] for i in range(0, len(sample_names), batch_size)])
+    else:
+        n_batches = (len(sample_names) + batch_size - 1) // batch_size
+
+        def _claimed():
+            while True:
+                b = claim()
+                if b is None or b >= n_batches:
+                    return
+                yield sample_names[b * batch_size:(b + 1) * batch_size]
+        batch_iter = _claimed()
     pending_writes = []
     with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
         def submit_decode(names):
@@ -523,12 +537,18 @@ def run_sweep_batched(args, extractor, sample_names: List[str], batch_size: int 
             except Exception as e:
                 return jobs, e
 
-        queue = [submit_decode(b) for b in batches[:2]]             # decode two batches ahead of the device
+        def refill(queue):
+            nb = next(batch_iter, None)
+            if nb is not None:
+                queue.append(submit_decode(nb))
+
+        queue = []
+        refill(queue)
+        refill(queue)                                               # decode two batches ahead of the device
         cur = staged_of(queue.pop(0)) if queue else None
-        for b in range(len(batches)):
+        while cur is not None:
             jobs, staged = cur
-            if b + 2 < len(batches):
-                queue.append(submit_decode(batches[b + 2]))
+            refill(queue)
             try:
                 if isinstance(staged, Exception):
                     raise staged
@@ -549,6 +569,21 @@ def run_sweep_batched(args, extractor, sample_names: List[str], batch_size: int 
         for f in pending_writes:
             f.result()
     return stats
+
+
+def shared_batch_counter(rank: int, world: int, host: Optional[str] = None, port: Optional[int] = None):
+    """-> claim() for ``run_sweep_batched``: a counter shared by all ranks of a torchrun job (a TCPStore hosted by rank 0 on
+    MASTER_PORT + 1; no process group, no collective).  Every call returns the next unclaimed batch index."""
+    import datetime
+    from torch.distributed import TCPStore
+    host = host or os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(port if port is not None else int(os.environ.get("MASTER_PORT", "29500")) + 1)
+    store = TCPStore(host, port, world, is_master=(rank == 0), timeout=datetime.timedelta(seconds=300))
+
+    def claim() -> int:
+        return int(store.add("agb_next_batch", 1)) - 1
+    claim.store = store                                          # keep the server alive as long as the closure lives
+    return claim
 
 
 def read_sample_names(args) -> List[str]:
@@ -590,6 +625,9 @@ def build_parser() -> argparse.ArgumentParser:
                    help="samples per device batch (not in the reference, which runs one sample per call); 1 = the "
                         "reference's per-sample loop")
     p.add_argument("--workers", type=int, default=8, help="host threads decoding / writing around the device batches")
+    p.add_argument("--static_shards", action="store_true",
+                   help="under torchrun: samples rank::world_size per GPU instead of batches claimed from a shared counter "
+                        "(the default with --batch_size > 1: a GPU that runs slower under the power cap claims fewer batches)")
     return p
 
 
@@ -612,10 +650,14 @@ def main(argv: Optional[List[str]] = None) -> int:
     validate_args(args)
     names = read_sample_names(args)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:                                            # one replica per GPU, samples rank::world
+    claim = None
+    if world > 1:                                            # one replica per GPU, no collective on the data path
         local = int(os.environ.get("LOCAL_RANK", str(rank)))
         args.device = f"cuda:{local}"
-        names = [names[i] for i in shard_indices(len(names), rank, world)]
+        if args.batch_size > 1 and not args.static_shards:
+            claim = shared_batch_counter(rank, world)        # batches of the global list, first come first served
+        else:
+            names = [names[i] for i in shard_indices(len(names), rank, world)]      # samples rank::world
     from .fusion import AffectGPTFusion
     from .registry import registry
     visual = registry.get_visual_encoder_class(args.visual_encoder)()
@@ -630,7 +672,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     extractor = MultimodalFeatureExtractor(visual, acoustic, fusion, device=args.device,
                                            mer_factory_output=args.mer_factory_output)
     if args.batch_size > 1:
-        stats = run_sweep_batched(args, extractor, names, batch_size=args.batch_size, workers=args.workers)
+        stats = run_sweep_batched(args, extractor, names, batch_size=args.batch_size, workers=args.workers, claim=claim)
     else:
         stats = run_sweep(args, extractor, names)
     print(f"[rank {rank}/{world}] " + ", ".join(f"{k}={v}" for k, v in stats.items()))

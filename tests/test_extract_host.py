@@ -218,3 +218,61 @@ def test_batched_sweep_falls_back_per_sample_when_the_device_batch_raises(tmp_pa
     st = X.run_sweep_batched(a, Flaky(), ["a", "b"], batch_size=bs, log=msgs.append)
     assert st["frame_success"] == 2 and st["face_success"] == 2 and st["multi_success"] == 2
     assert any("sample by sample" in m for m in msgs)
+
+
+def _claim_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    claim = X.shared_batch_counter(rank, world)
+    got = []
+    for _ in range(50):
+        b = claim()
+        if b >= 12:
+            break
+        got.append(b)
+        if rank == 1:
+            import time
+            time.sleep(0.005)                                  # the "slow GPU": must end up with fewer batches
+    q.put((rank, got))
+    import time
+    time.sleep(0.5)                                            # rank 0 hosts the store: outlive the other rank's last call
+
+
+def test_dynamic_shards_claim_every_batch_exactly_once(tmp_path):
+    """torchrun sweep with --batch_size > 1: batches of the global sample list are claimed from a counter all ranks share
+    (TCPStore on MASTER_PORT + 1): every batch exactly once, the slower rank fewer of them."""
+    import multiprocessing as mp
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_claim_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res[0] + res[1]) == list(range(12))
+    assert len(res[0]) > len(res[1])
+
+
+def test_batched_sweep_with_a_claim_function_covers_the_same_samples(tmp_path):
+    """run_sweep_batched(claim=...) over the GLOBAL list: two "ranks" sharing one counter write, between them, exactly the
+    files one rank writes alone (host logic with the stub extractor)."""
+    names = [f"s{i:02d}" for i in range(11)]
+    out = {}
+    for mode in ("alone", "shared"):
+        args = X.build_parser().parse_args(["--dataset", "meld", "--modality", "audio", "--audio_root", str(tmp_path / "a"),
+                                            "--save_root", str(tmp_path / mode), "--quiet"])
+        os.makedirs(tmp_path / "a", exist_ok=True)
+        for n in names:
+            (tmp_path / "a" / f"{n}.wav").write_bytes(b"x")
+        if mode == "alone":
+            X.run_sweep_batched(args, BatchStub(), names, batch_size=3, workers=2, log=lambda *_: None)
+        else:
+            counter = iter(range(100))
+            claim = lambda: next(counter)                                             # noqa: E731 - one shared counter
+            for _rank in range(2):                                                    # second "rank" finds nothing left
+                X.run_sweep_batched(args, BatchStub(), names, batch_size=3, workers=2, log=lambda *_: None, claim=claim)
+        out[mode] = sorted(os.path.relpath(os.path.join(d, f), tmp_path / mode) for d, _, fs in os.walk(tmp_path / mode) for f in fs)
+    assert out["alone"] == out["shared"] and len(out["alone"]) == len(names)

@@ -6,7 +6,9 @@
 * Inputs are generated ON THE DEVICE per sample from ``seed = clip_index``: 8 frames + 8 face crops (uint8
   224 x 224) and a 4 s waveform cut into the reference's 8 x 2 s segments (ImageBind/data.py:70-78 rule, computed by
   affectgpt_b200.sampling).  A sample therefore does not depend on the rank or the batch it lands in.
-* Rank r takes samples r::W (the sweep CLI's sharding); no collective on the data path.
+* Sharding as in the sweep CLI (`python -m affectgpt_b200.extract` under torchrun): batches of 64 consecutive samples are
+  claimed from a counter all ranks share (extract.shared_batch_counter), so a GPU that runs slower under the power cap
+  claims fewer batches; `--static-shards` gives rank r the batches r::W instead.  No collective on the data path.
 * Every sample writes the reference's four files - frame [8,768], face [8,768], audio [8,1024], multi [1024], fp32 .npy -
   into ``save_root/<dataset>/{frame_*, face_*, audio_*, multi_*}/<name>.npy`` (extract.save_dirs) from a writer pool,
   while the next batch is on the GPU (two pinned host slots per rank).
@@ -38,6 +40,7 @@ ap.add_argument("--save-root", default="/tmp/agb_c5")
 ap.add_argument("--writers", type=int, default=8)
 ap.add_argument("--cpu-samples", type=int, default=2)
 ap.add_argument("--keep", action="store_true", help="leave the written files on disk")
+ap.add_argument("--static-shards", action="store_true", help="batches rank::world instead of the shared counter")
 args = ap.parse_args()
 
 RANK, WORLD = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -68,8 +71,14 @@ def main():
     graph = agb.GraphedClipBatch(model, B, 8, 8, with_faces=True, device=DEV, frame_dtype=torch.uint8)
     xargs = X.build_parser().parse_args(["--dataset", "mercaptionplus", "--save_root", args.save_root, "--quiet"])
     dirs = X.save_dirs(xargs)                 # the sources are synthetic: no --video_root / --face_root / --audio_root to validate
-    mine = list(range(RANK, args.samples, WORLD))
-    batches = [mine[i:i + B] for i in range(0, len(mine), B)]
+    n_batches = (args.samples + B - 1) // B
+    batch_of = lambda b: list(range(b * B, min((b + 1) * B, args.samples)))          # noqa: E731
+    if WORLD > 1 and not args.static_shards:
+        claim = X.shared_batch_counter(RANK, WORLD)
+    else:
+        _it = iter(range(RANK, n_batches, WORLD))
+        claim = lambda: next(_it, n_batches)                                          # noqa: E731
+    own_batches = []
     widths = {"frame": (8, 768), "face": (8, 768), "audio": (8, 1024), "multi": (1024,)}
     keys = {"frame": "frame_hiddens", "face": "face_hiddens", "audio": "audio_hiddens", "multi": "multi_hiddens"}
     host = [{k: torch.empty((B,) + w, dtype=torch.float32).pin_memory() for k, w in widths.items()} for _ in range(2)]
@@ -103,11 +112,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up + device-bound rate of the same loop (generation + encoders, no D2H, no files)
-    run_batch(batches[0])
+    run_batch(batch_of(RANK % n_batches))
     barrier()
     t0 = time.perf_counter()
     n_dev = 0
-    for b in batches[1:9]:
+    for k in range(1, 9):
+        b = batch_of((RANK + k * WORLD) % n_batches)
         if len(b) == B:
             run_batch(b)
             n_dev += B
@@ -121,7 +131,14 @@ def main():
     futs = []
     with ThreadPoolExecutor(max_workers=args.writers) as pool:
         slot_busy = [None, None]
-        for bi, idxs in enumerate(batches):
+        bi = -1
+        while True:
+            b = claim()
+            if b >= n_batches:
+                break
+            own_batches.append(b)
+            idxs = batch_of(b)
+            bi += 1
             slot = bi % 2
             if slot_busy[slot] is not None:
                 slot_busy[slot].result()                               # the writer has drained this host slot
@@ -138,13 +155,15 @@ def main():
             f.result()
     torch.cuda.synchronize()
     t_end = time.perf_counter()
-    own = {"seconds": t_end - t_start, "steady_seconds": t_end - t_first, "samples": len(mine), "device_bound_rate": dev_rate}
+    n_own = sum(len(batch_of(b)) for b in own_batches)
+    own = {"seconds": t_end - t_start, "steady_seconds": t_end - (t_first or t_start), "samples": n_own, "device_bound_rate": dev_rate}
 
     # ---- determinism probe: 4 samples of the NEXT rank's shard recomputed here vs that rank's files
     barrier()
-    other = (RANK + 1) % WORLD
-    probe = list(range(other, args.samples, WORLD))[:: max(1, len(mine) // 4)][:4]
-    run_batch((probe + mine[:B])[:B])
+    mine_set = set(own_batches)
+    foreign = [b for b in range(n_batches) if b not in mine_set] or list(range(n_batches))
+    probe = [batch_of(b)[0] for b in foreign[:: max(1, len(foreign) // 4)][:4]]        # samples some OTHER rank wrote
+    run_batch((probe + batch_of(0))[:B])
     out = {k: graph.outputs[v][:len(probe)].float().cpu().numpy() for k, v in keys.items()}
     same = True
     for j, idx in enumerate(probe):
@@ -168,6 +187,8 @@ def main():
                "device_bound_samples_per_s": sum(float(r[3]) for r in allr),
                "host_pipeline_loss": 1.0 - (total - WORLD * B) / steady / max(sum(float(r[3]) for r in allr), 1e-9),
                "files_written": int(sum(float(r[4]) for r in allr)), "bytes_written": int(sum(float(r[5]) for r in allr)),
+               "sharding": "static (batches rank::world)" if args.static_shards or WORLD == 1 else "dynamic (batches claimed from a shared counter)",
+               "per_rank_samples": [int(float(r[2])) for r in allr],
                "per_rank_seconds": [round(float(r[0]), 2) for r in allr],
                "per_rank_device_bound": [round(float(r[3]), 1) for r in allr],
                "cross_rank_files_bit_identical": all(float(r[6]) == 1.0 for r in allr),
