@@ -125,8 +125,12 @@ int stage_faces_u8(const uint8_t* faces, int64_t n_src, int h, int w, const int*
                    cudaStream_t s) {
   AGB_REQUIRE(faces && idx_dev && out && n_src > 0 && n_src < (1ll << 31) && h > 0 && w > 0 && T > 0,
               "stage_faces: bad arguments");
-  static int* bad_dev = nullptr;            // one 4-byte counter per process (staging is not on the graph-captured path)
-  if (bad_dev == nullptr) AGB_CHECK_CUDA(cudaMalloc(&bad_dev, sizeof(int)));
+  static int* bad_by_device[64] = {};       // one 4-byte counter per device (staging is not on the graph-captured path)
+  int dev = 0;
+  AGB_CHECK_CUDA(cudaGetDevice(&dev));
+  AGB_REQUIRE(dev >= 0 && dev < 64, "stage_faces: device index out of range");
+  if (bad_by_device[dev] == nullptr) AGB_CHECK_CUDA(cudaMalloc(&bad_by_device[dev], sizeof(int)));
+  int* bad_dev = bad_by_device[dev];
   AGB_CHECK_CUDA(cudaMemsetAsync(bad_dev, 0, sizeof(int), s));
   {
     LaunchTimer timer(PROF_FRONTEND, 0.0, (double)T * (4.0 * 3 * 224 * 224 + 3.0 * 224 * 224), s);

@@ -582,7 +582,17 @@ def shared_batch_counter(rank: int, world: int, host: Optional[str] = None, port
 
     def claim() -> int:
         return int(store.add("agb_next_batch", 1)) - 1
+
+    def finish(poll_s: float = 0.05, timeout_s: float = 3600.0) -> None:
+        """Call once per rank after its last claim: rank 0 hosts the counter and must not exit before the others are done."""
+        import time
+        store.add("agb_done", 1)
+        if rank == 0:
+            t0 = time.time()
+            while int(store.add("agb_done", 0)) < world and time.time() - t0 < timeout_s:
+                time.sleep(poll_s)
     claim.store = store                                          # keep the server alive as long as the closure lives
+    claim.finish = finish
     return claim
 
 
@@ -676,6 +686,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     else:
         stats = run_sweep(args, extractor, names)
     print(f"[rank {rank}/{world}] " + ", ".join(f"{k}={v}" for k, v in stats.items()))
+    if claim is not None:
+        claim.finish()
     return 0
 
 

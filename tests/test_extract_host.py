@@ -233,8 +233,7 @@ def _claim_worker(rank, world, port, q):
             import time
             time.sleep(0.005)                                  # the "slow GPU": must end up with fewer batches
     q.put((rank, got))
-    import time
-    time.sleep(0.5)                                            # rank 0 hosts the store: outlive the other rank's last call
+    claim.finish()                                             # rank 0 hosts the store: it waits here for the other rank
 
 
 def test_dynamic_shards_claim_every_batch_exactly_once(tmp_path):
