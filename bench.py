@@ -20,7 +20,8 @@
 Multi-GPU: one process per GPU (torchrun), clips sharded across ranks, one NCCL all_gather_into_tensor of the fused tokens
 per step on a side stream (parallel.ClipGather: step i's gather overlaps step i+1's encoders; the timed region ends after
 the last gather).  Every rank then recomputes two clips of ANOTHER rank's shard locally and compares them with the gathered
-rows bit for bit (`multi_gpu_parity`); `per_rank` lists every rank's own step time and SM clock.
+rows bit for bit (`multi_gpu_parity`); `per_rank` lists every rank's own step time and SM clock.  `--balance` (opt-in)
+splits the global batch in proportion to each GPU's measured speed instead of equally (`balance` in the JSON line).
 """
 from __future__ import annotations
 
