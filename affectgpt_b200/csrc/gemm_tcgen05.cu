@@ -535,7 +535,9 @@ int launch(const Maps& m, const KParams& kp, cudaStream_t stream) {
 // fused 123.7 ms vs separate LayerNorm passes 120.6 ms, although the LayerNorm category drops from 10.2 to 1.9 ms and 51 GB
 // of HBM reads per step disappear.  The step runs against the 1 kW power cap, where time follows joules: the stand-alone
 // pass costs 0.118 J (profiles/r02_energy_probe.jsonl), of which only the DRAM read (~0.02 J) is saved, and the tail costs
-// the GEMM more than that (168 registers with spills, epilogue warps busy while the tensor pipe waits).  Kept opt-in and
+// the GEMM more than that (168 registers with spills, epilogue warps busy while the tensor pipe waits).  A variant with
+// four dedicated LayerNorm warps (512 threads, 128 registers, arrivals posted one tile late with cp.async.bulk.wait_group
+// NCH so that neither the epilogue nor the MMA warp ever waits) was bit-identical too and worse: 123.2 vs 113.4 ms.  Kept opt-in and
 // tested for bit-identity (tests/test_gpu_kernels.py); read per call so one process can capture a graph per setting.
 bool fused_ln_on() {
   const char* e = getenv("AGB_FUSED_LN");
