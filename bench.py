@@ -68,6 +68,17 @@ def gemm_traffic_per_launch():
         return None
 
 
+def gpu_energy_mj(index: int):
+    """NVML total-energy counter of one GPU in mJ (None when NVML is unavailable).  Read on both sides of the timed
+    region: the step runs against the power cap, so joules per step is the quantity the step time follows."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        return int(pynvml.nvmlDeviceGetTotalEnergyConsumption(pynvml.nvmlDeviceGetHandleByIndex(index)))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -406,7 +417,10 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()                               # every rank samples its own GPU (per_rank in the JSON line)
     l0 = E.launch_count()
+    j0, tj0 = gpu_energy_mj(local), time.perf_counter()
     ms_dev = timed(step_resident, args.steps, "resident")
+    j1, tj1 = gpu_energy_mj(local), time.perf_counter()
+    joules_per_step = (j1 - j0) / 1e3 / args.steps if (j0 is not None and j1 is not None and j1 > j0) else None
     launches = (graphed[2].kernels_per_replay * args.steps) if use_graph else (E.launch_count() - l0)
     if args.only_resident:
         if rank == 0:
@@ -499,6 +513,11 @@ def main():
                      "layernorm_gbs": (prof["layernorm"]["bytes"] / (prof["layernorm"]["ms"] / 1e3) / 1e9) if prof["layernorm"]["ms"] > 0 else 0.0,
                      "frontend_gbs": (prof["frontend"]["bytes"] / (prof["frontend"]["ms"] / 1e3) / 1e9) if prof["frontend"]["ms"] > 0 else 0.0},
         "clocks": clk,
+        "energy": {"joules_per_step": joules_per_step, "joules_per_clip": (joules_per_step / B if joules_per_step else None),
+                   "avg_w": (joules_per_step * args.steps / (tj1 - tj0) if joules_per_step else None),
+                   "wall_s_between_reads": tj1 - tj0,
+                   "source": "NVML total-energy counter of this rank's GPU read on both sides of the timed device-resident "
+                             "steps (wall clock between the reads includes the two barriers; the counter is coarse for few steps)"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and (NF, NS, FACES) == (8, 8, False):   # the CPU sample is C2-shaped
         cps, cores, dt = cpu_oracle_clips_per_sec(args.cpu_clips, warmup=1)
