@@ -96,6 +96,24 @@ out.append(probe("gemm FC2  M=131584 N=1024 K=4096 += fp32", lambda: ops.gemm_in
 resid.normal_(generator=g)
 out.append(probe("layernorm 131584 x 1024 fp32 -> bf16", lambda: ops.layernorm(resid, gam, bet), bytes_=M * 1024 * 6.0, step_launches=47))
 out.append(probe("attention 512 x 16 heads x 257 tokens", lambda: ops.attention(qkv, 512, 257, 257), flops=4.0 * 512 * 16 * 257 * 257 * 64, step_launches=23))
+# ---- HuBERT-side kernels at C2 (512 segments)
+del x, h1, qkv, o_qkv, o_h1, resid
+torch.cuda.empty_cache()
+Mh = 512 * 100
+qkv_h = (rn(Mh, 3072) * 0.5).bfloat16()
+out.append(probe("attention 512 x 16 heads x 99 frames (HuBERT)", lambda: ops.attention(qkv_h, 512, 100, 99), flops=4.0 * 512 * 16 * 99 * 99 * 64, step_launches=24))
+wav = rn(512, 32000) * 0.1
+c0w, c0b = rn(512, 1, 10) * 0.3, rn(512) * 0.05
+g512, b512 = 1 + 0.1 * rn(512), 0.1 * rn(512)
+out.append(probe("conv0 + LayerNorm(512) + GELU, 512 segments (tcgen05)", lambda: ops.conv0(wav, c0w, c0b, g512, b512, "layer", 8),
+                 bytes_=512 * (32000 * 4.0 + 6400 * 512 * 2.0), step_launches=1))
+xc = (rn(512 * 3200, 512) * 0.5).bfloat16()
+out.append(probe("ln512 + GELU over 1.64 M rows bf16 (conv stack layer 1)", lambda: ops.layernorm512_bf16(xc, g512, b512), bytes_=512 * 3200 * 512 * 4.0, step_launches=1))
+x16 = (rn(Mh, 1024) * 0.5).bfloat16(); wp = (rn(1024, 8192) * 0.01).bfloat16(); pb = rn(1024) * 0.05; rs = rn(Mh, 1024)
+out.append(probe("positional conv k=128 g=16 as GEMM, 512 x 99 (+= fp32)", lambda: ops.posconv_residual(x16, wp, pb, rs, 512, 100, 99),
+                 flops=2.0 * 512 * 99 * 1024 * 64 * 128, step_launches=1))
+del qkv_h, xc, x16, wp, rs
+torch.cuda.empty_cache()
 # ---- copy kernel as the HBM reference point
 src = torch.empty(1 << 30, dtype=torch.bfloat16, device=DEV); dst = torch.empty_like(src)
 out.append(probe("torch copy 2 GiB bf16 (HBM read+write)", lambda: dst.copy_(src), bytes_=4.0 * (1 << 30)))
